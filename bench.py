@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: algebraic-distance relaxation throughput (incidence nnz * R * iters / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one full relaxation (load, `sweeps` x (node half, edge half, fused rescale),
+store) of the BASELINE.json configs[1] workload: synthetic power-law hypergraph, 1M nodes /
+500K edges / ~10M incidences, R = 32 trial columns, 20 sweeps.  Prints ONE JSON line.
+
+`value`     device-resident: vectors and incidence already in HBM when the timed region starts.
+`e2e`       the same step through the host-buffer C-ABI call (hge_incidence_create +
+            hge_algdist_run with HGE_MEM_HOST): pinned host -> device copies of the incidence
+            arrays and the initial vectors and the device -> host copy of the result are inside
+            the timed region.
+`roofline`  the half-sweep kernel: algorithmic bytes per launch / its mean launch
+            duration measured with CUDA events on the launch stream, against the measured HBM
+            copy peak in MEASURED_PEAKS.json.
+`cpu_baseline` the oracle port (oracle/port.py, scipy f64, one core) on a bounded sample of the
+            same workload, timed on this box's host cores.  Reported, not the target.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2": dict(kind="power_law", num_nodes=1000000, num_edges=500000, num_incidences=10000000,
+               R=32, sweeps=20, seed=1234,
+               name="synthetic power-law hypergraph 1M nodes / 500K edges / 10M incidences, R=32, 20 sweeps"),
+    # small variant for quick checks (not a bench line)
+    "mini": dict(kind="power_law", num_nodes=100000, num_edges=50000, num_incidences=1000000,
+                 R=32, sweeps=20, seed=1234, name="1/10-scale config 2 (debug)"),
+}
+
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def log(*a):
+  print(*a, file=sys.stderr, flush=True)
+
+
+def build_workload(spec, cache=True):
+  from hypergraphembedding_b200 import synthetic
+  key = "hge_%s_%d_%d_%d_%d.npz" % (spec["kind"], spec["num_nodes"], spec["num_edges"],
+                                   spec["num_incidences"], spec["seed"])
+  path = os.path.join(os.environ.get("HGE_CACHE_DIR", "/tmp"), key)
+  import scipy.sparse as sps
+  if cache and os.path.exists(path):
+    z = np.load(path)
+    A = sps.csr_matrix((np.ones(len(z["indices"]), dtype=bool), z["indices"], z["indptr"]),
+                       shape=tuple(z["shape"]))
+  else:
+    t = time.time()
+    A = synthetic.power_law_hypergraph(spec["num_nodes"], spec["num_edges"], spec["num_incidences"],
+                                       seed=spec["seed"])
+    log("generated %s in %.1f s" % (spec["name"], time.time() - t))
+    if cache:
+      try:
+        np.savez(path, indices=A.indices, indptr=A.indptr, shape=np.asarray(A.shape))
+      except OSError:
+        pass
+  B = A.T.tocsr()
+  B.sort_indices()
+  return A, B
+
+
+def algorithmic_bytes_per_sweep(N, E, nnz, R):
+  """each half-sweep gathers one R-row (4R bytes) and reads one column
+  id (4 bytes) per incidence and reads + writes each owned row once."""
+  return 2 * nnz * (4 * R + 4) + 2 * (N + E) * 4 * R
+
+
+def hbm_peak():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    try:
+      return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+      pass
+  return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+  """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+  QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+           "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+           "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index=0):
+    self.index = index
+    self.rows = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+          stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if not self.proc:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[0]))
+        mx.append(float(r[1]))
+      except (ValueError, IndexError):
+        continue
+      for name, flag in zip(names, r[3:7]):
+        if flag.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_port(A, B, spec, sweeps):
+  """The oracle port on a bounded sample: `sweeps` sweeps of the full workload, scipy f64."""
+  from hypergraphembedding_b200 import synthetic
+  from oracle import port
+  xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], spec["R"], seed=0)
+  t = time.time()
+  port.algdist_vectorised(A, B, xn0, xe0, sweeps)
+  dt = time.time() - t
+  return A.nnz * spec["R"] * sweeps / dt, dt
+
+
+def run_reference(args, spec):
+  """--impl reference: the reference's CPU implementation of the path.  The reference is pure
+  Python and its tree does not travel to the GPU box, so this is the oracle port of it."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  A, B = build_workload(spec)
+  sample_sweeps = 2
+  for _ in range(max(0, min(args.warmup, 1))):
+    cpu_baseline_port(A, B, spec, 1)
+  vals, secs = [], []
+  for _ in range(max(1, args.steps)):
+    v, dt = cpu_baseline_port(A, B, spec, sample_sweeps)
+    vals.append(v)
+    secs.append(dt)
+  value = float(np.mean(vals))
+  sample = "%d of %d sweeps of the full workload per step" % (sample_sweeps, spec["sweeps"])
+  out = {
+      "impl": "reference", "metric": "alg-dist incidence nnz*R*iters/sec", "value": value,
+      "unit": "nnz*R*iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+      "config": {"workload": spec["name"], "nnz": int(A.nnz), "sample": sample},
+      "cpu_baseline": {"value": value, "unit": "nnz*R*iters/s", "cores": 1, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": value, "unit": "nnz*R*iters/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(out), flush=True)
+
+
+def run_ours(args, spec):
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import _native, synthetic
+  from hypergraphembedding_b200 import algebraic_distance as ad
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world > 1:
+    raise SystemExit("multi-GPU bench lives in bench_multi (wired up below once sharding lands)")
+  torch.cuda.set_device(local_rank)
+  ctx = _native.default_context(local_rank)
+
+  A, B = build_workload(spec)
+  N, E = A.shape
+  nnz, R, sweeps = int(A.nnz), spec["R"], spec["sweeps"]
+  xn0, xe0 = synthetic.legacy_initial_vectors(N, E, R, seed=0)
+
+  # ---- device-resident arm ---------------------------------------------------------------
+  a_ptr = torch.from_numpy(A.indptr.astype(np.int64)).cuda()
+  a_idx = torch.from_numpy(A.indices.astype(np.int32)).cuda()
+  b_ptr = torch.from_numpy(B.indptr.astype(np.int64)).cuda()
+  b_idx = torch.from_numpy(B.indices.astype(np.int32)).cuda()
+  inc = _native.Incidence(ctx, N, E, a_ptr, a_idx, b_ptr, b_idx)
+  xn_init = torch.from_numpy(xn0).cuda()
+  xe_init = torch.from_numpy(xe0).cuda()
+  xn = torch.empty_like(xn_init)
+  xe = torch.empty_like(xe_init)
+
+  def step_device():
+    xn.copy_(xn_init)
+    xe.copy_(xe_init)
+    _native.algdist_run(ctx, inc, xn, xe, sweeps)
+
+  for _ in range(args.warmup):
+    step_device()
+  torch.cuda.synchronize()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  launches0 = ctx.launch_count
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  ev0.record()
+  for _ in range(args.steps):
+    step_device()
+  ev1.record()
+  torch.cuda.synchronize()
+  total_ms = ev0.elapsed_time(ev1)
+  launches = ctx.launch_count - launches0
+  clocks = sampler.stop()
+  ms_per_step = total_ms / args.steps
+  value = nnz * R * sweeps / (ms_per_step * 1e-3)
+
+  # ---- per-launch duration of the half-sweep kernel (stepwise API, same stream) -------------
+  st = _native.AlgDistState(ctx, inc, R, sweeps)
+  half_ms = []
+  for rep in range(max(1, min(args.steps, 3))):
+    xn.copy_(xn_init)
+    xe.copy_(xe_init)
+    st.load(xn, xe)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * sweeps + 1)]
+    evs[0].record()
+    for t in range(sweeps):
+      st.node_half(t)
+      evs[2 * t + 1].record()
+      st.edge_half(t)
+      evs[2 * t + 2].record()
+    torch.cuda.synchronize()
+    half_ms.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(2 * sweeps))
+  st.close()
+  half_ms = np.asarray(half_ms)
+  node_ms = float(half_ms[0::2].mean())
+  edge_ms = float(half_ms[1::2].mean())
+  mean_half_ms = float(half_ms.mean())
+  bytes_per_launch = algorithmic_bytes_per_sweep(N, E, nnz, R) / 2.0
+  achieved = bytes_per_launch / (mean_half_ms * 1e-3) / 1e9
+  peak, peak_src = hbm_peak()
+
+  # ---- end-to-end arm: host buffers through the C ABI --------------------------------------
+  pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+  h_aptr, h_aidx = pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32))
+  h_bptr, h_bidx = pin(B.indptr.astype(np.int64)), pin(B.indices.astype(np.int32))
+  h_xn0, h_xe0 = pin(xn0), pin(xe0)
+  h_xn, h_xe = pin(np.empty_like(xn0)), pin(np.empty_like(xe0))
+
+  def step_host():
+    h_xn.copy_(h_xn0)
+    h_xe.copy_(h_xe0)
+    inc_h = _native.Incidence(ctx, N, E, h_aptr.numpy(), h_aidx.numpy(), h_bptr.numpy(),
+                              h_bidx.numpy())
+    _native.algdist_run(ctx, inc_h, h_xn.numpy(), h_xe.numpy(), sweeps)
+    inc_h.close()
+
+  e2e_steps = max(1, min(args.steps, 5))
+  for _ in range(min(args.warmup, 2)):
+    step_host()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    step_host()
+  torch.cuda.synchronize()
+  e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+  h2d = (h_aptr.numel() + h_bptr.numel()) * 8 + (h_aidx.numel() + h_bidx.numel()) * 4 + \
+      (h_xn0.numel() + h_xe0.numel()) * 4
+  d2h = (h_xn.numel() + h_xe.numel()) * 4
+
+  # parity spot check of what was just timed (device arm vs host arm must agree bit for bit)
+  same = bool(np.array_equal(xn.cpu().numpy(), h_xn.numpy()))
+
+  cpu_sweeps = 2
+  cpu_value, cpu_dt = cpu_baseline_port(A, B, spec, cpu_sweeps)
+
+  out = {
+      "metric": "alg-dist incidence nnz*R*iters/sec", "value": value, "unit": "nnz*R*iters/s",
+      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": spec["name"], "nodes": N, "edges": E, "nnz": nnz, "R": R,
+                 "sweeps": sweeps, "seed": spec["seed"],
+                 "l2": "no flush: per-step working set (vectors %d MB + incidence %d MB) exceeds the 126 MB L2"
+                       % ((N + E) * R * 4 >> 20, (2 * nnz * 4) >> 20),
+                 "device_vs_host_arm_identical": same},
+      "roofline": {"bound": "hbm", "kernel": "k_half_sweep<8>", "achieved": achieved, "peak": peak,
+                   "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                   "bytes_per_launch": bytes_per_launch, "ms_per_launch": mean_half_ms,
+                   "node_half_ms": node_ms, "edge_half_ms": edge_ms,
+                   "frac_of_nominal_8TBs": achieved / 8000.0},
+      "cpu_baseline": {"value": cpu_value, "unit": "nnz*R*iters/s", "cores": 1, "kind": "port",
+                       "sample": "%d of %d sweeps of the full workload, scipy f64 (%.1f s)"
+                                 % (cpu_sweeps, sweeps, cpu_dt),
+                       "host_cores": os.cpu_count()},
+      "e2e": {"value": nnz * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
+              "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+      "gpu_launches": int(launches),
+      "clocks": clocks,
+  }
+  print(json.dumps(out), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+  args = ap.parse_args()
+  spec = WORKLOADS[args.workload]
+  if args.impl == "reference":
+    run_reference(args, spec)
+  else:
+    run_ours(args, spec)
+
+
+if __name__ == "__main__":
+  main()

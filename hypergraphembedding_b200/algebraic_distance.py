@@ -1,0 +1,72 @@
+"""Drop-in for the reference's ``hypergraph_embedding/algebraic_distance.py``.
+
+``EmbedAlgebraicDistance`` keeps the reference signature and semantics
+(algebraic_distance.py:126-175): ids are compressed by sorted order, the initial vectors are
+drawn from the process-global legacy numpy RNG (nodes first, then edges, :140-141), the
+relaxation runs for ``iterations`` sweeps, and the result is a ``HypergraphEmbedding`` keyed
+by the original ids with ``method_name == "AlgebraicDistance"`` (:168).
+
+The sweeps themselves run in libhge_b200.so (csrc/hge_algdist.cu) in fp32; there is no CPU
+implementation in this package.
+"""
+import logging
+
+import numpy as np
+
+from . import _native
+from .hypergraph_pb2 import HypergraphEmbedding
+from .hypergraph_util import compressed_incidence, csr_arrays
+
+log = logging.getLogger()
+
+
+def relax(incidence, node_vectors, edge_vectors, iterations, ctx=None, lohi=None):
+  """Runs the relaxation in place on fp32 [N, R] / [E, R] arrays (numpy on the host, or torch
+  CUDA tensors that stay on the device).  ``incidence`` is a ``_native.Incidence``."""
+  ctx = ctx or incidence.ctx
+  return _native.algdist_run(ctx, incidence, node_vectors, edge_vectors, iterations, lohi=lohi)
+
+
+def make_incidence(n2e_csr, e2n_csr=None, ctx=None):
+  """Uploads a scipy N x E incidence matrix (and its E x N counterpart, default: transpose)."""
+  ctx = ctx or _native.default_context()
+  if e2n_csr is None:
+    e2n_csr = n2e_csr.T.tocsr()
+  a_ptr, a_idx = csr_arrays(n2e_csr)
+  b_ptr, b_idx = csr_arrays(e2n_csr)
+  return _native.Incidence(ctx, n2e_csr.shape[0], n2e_csr.shape[1], a_ptr, a_idx, b_ptr, b_idx)
+
+
+def EmbedAlgebraicDistance(hypergraph,
+                           dimension,
+                           iterations=20,
+                           run_in_parallel=True,
+                           disable_pbar=False):
+  """algebraic_distance.py:126-175.  ``run_in_parallel`` / ``disable_pbar`` are accepted for
+  compatibility; the work is one GPU call either way."""
+  del run_in_parallel, disable_pbar
+  node_ids, edge_ids, node2edges = compressed_incidence(hypergraph)
+  num_nodes = len(node_ids)   # == max(compressed ids) + 1, algebraic_distance.py:135-136
+  num_edges = len(edge_ids)
+
+  log.info("Random Initialization")
+  # all embeddings are in 0-1 interval; same draws as the reference (f64, nodes then edges)
+  node_embeddings = np.random.random((num_nodes, dimension)).astype(np.float32)
+  edge_embeddings = np.random.random((num_edges, dimension)).astype(np.float32)
+
+  log.info("Uploading node-edge incidence")
+  incidence = make_incidence(node2edges)
+  try:
+    log.info("Performing iterations of Algebraic Distance Calculations")
+    relax(incidence, node_embeddings, edge_embeddings, iterations)
+  finally:
+    incidence.close()
+
+  embedding = HypergraphEmbedding()
+  embedding.dim = dimension
+  embedding.method_name = "AlgebraicDistance"
+  for idx, node_id in enumerate(node_ids.tolist()):
+    embedding.node[node_id].values.extend(node_embeddings[idx, :].tolist())
+  for idx, edge_id in enumerate(edge_ids.tolist()):
+    embedding.edge[edge_id].values.extend(edge_embeddings[idx, :].tolist())
+  return embedding

@@ -1,0 +1,908 @@
+// Algebraic-distance relaxation on sm_100a.
+//
+// Reference arithmetic (algebraic_distance.py:34-123), with A the N x E incidence matrix,
+// w_E[e] = 1 / deg(e), w_N[n] = 1 / deg(n), s_N = A w_E, s_E = A^T w_N:
+//     XN' = (XN + (A  (XE  * w_E)) / s_N) / 2          node half, OLD edge rows
+//     XE' = (XE + (A^T (XN' * w_N)) / s_E) / 2          edge half, NEW node rows
+//     lo/hi = per-column min/max over XN' and XE' jointly; X <- (X' - lo) / (hi - lo)
+//
+// Storage ("Y-space").  Rows are kept pre-multiplied by their own weight, Y[r] = X'[r] * w[r],
+// fp32 row-major with the row padded to a multiple of 4 floats (ld).  The gather of a
+// half-sweep is then a plain sum of neighbour rows (no per-incidence weight lookup), and a
+// row's own value is recovered as Y[r] * deg(r).  The rescale is lazy: X' is what is stored,
+// and the affine map of sweep t-1, (lo, 1/(hi-lo)), is applied when sweep t reads a row.  It
+// commutes with the gather:  sum_b w_b (X'_b - lo) inv / s = inv (acc / s - lo),  so it costs
+// two FMAs per row instead of a full read+write pass per sweep.  Per-column min / max of a
+// sweep are accumulated by the two half-sweep kernels with warp shuffles, shared memory and
+// one atomicMin / atomicMax per column per block on order-preserving int32 encodings.
+//
+// Every row is updated in place by the one sub-warp (or the last chunk-warp) that owns it, so
+// a half-sweep reads each own row once, writes it once, and gathers nnz neighbour rows.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "hge_incidence.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ----------------------------------------------------------------------------------------
+// setup kernels
+// ----------------------------------------------------------------------------------------
+
+__global__ void k_row_degree(int32_t rows, const int64_t* __restrict__ ptr,
+                             int32_t* __restrict__ deg) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    deg[r] = (int32_t)(ptr[r + 1] - ptr[r]);
+}
+
+// invs[r] = 1 / sum_{b in row r} 1 / other_deg[b], accumulated in f64 (one warp per row).
+__global__ void k_row_invs(int32_t rows, const int64_t* __restrict__ ptr,
+                           const int32_t* __restrict__ idx,
+                           const int32_t* __restrict__ other_deg, float* __restrict__ invs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += nw) {
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    double s = 0.0;
+    for (int64_t p = b + lane; p < e; p += 32) s += 1.0 / (double)other_deg[idx[p]];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    if (lane == 0) invs[r] = (float)(1.0 / s);
+  }
+}
+
+__global__ void k_fill_minmax(int32_t* mm, int slots, int ld) {
+  const int n = slots * 2 * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    mm[i] = ((i / ld) & 1) ? INT32_MIN : INT32_MAX;  // [slot][0]=min, [slot][1]=max
+}
+
+// X (dense [rows, R]) -> Y (padded [rows, ld]),  Y = X / deg.
+__global__ void k_load_rows(int64_t rows, int R, int ld, const float* __restrict__ x,
+                            const int32_t* __restrict__ deg, float* __restrict__ y) {
+  const int64_t total = rows * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = (int)(i - r * ld);
+    float v = 0.f;
+    if (c < R) v = x[r * R + c] * __frcp_rn((float)deg[r]);
+    y[i] = v;
+  }
+}
+
+// Y -> X with the affine map of the last sweep (mm == nullptr: identity).
+__global__ void k_store_rows(int64_t rows, int R, int ld, const float* __restrict__ y,
+                             const int32_t* __restrict__ deg, const int32_t* __restrict__ mm,
+                             float* __restrict__ x) {
+  const int64_t total = rows * R;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / R;
+    const int c = (int)(i - r * R);
+    float v = y[r * ld + c] * (float)deg[r];
+    if (mm) {
+      const float lo = hge_dec(mm[c]);
+      const float hi = hge_dec(mm[ld + c]);
+      v = (v - lo) / (hi - lo);
+    }
+    x[i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// the half-sweep kernel
+// ----------------------------------------------------------------------------------------
+
+struct HalfSweepArgs {
+  const int32_t* idx;          // CSR column ids of this half
+  const float4* yg;            // rows that are gathered        [*, ld4]
+  float4* yo;                  // rows that are owned / updated [rows, ld4]
+  const HgeLightItem* light;
+  int64_t n_light;
+  const HgeHeavyRow* hrows;
+  const int2* chunks;
+  int32_t n_chunks;
+  int32_t n_hrows;
+  int32_t chunk_sz;
+  float4* partials;            // [n_partials, ld4]
+  int32_t* counters;           // [slabs, n_hrows]
+  const int32_t* mm_prev;      // affine of the previous sweep, or nullptr (identity)
+  int32_t* mm_cur;             // min / max slots of this sweep
+  int32_t gather_affine;       // 1: gathered rows carry the previous sweep's affine (node half)
+  int32_t raw_out;             // 1: write the raw gathered sums to raw[rows, ld4] (sharded edge half)
+  float4* raw;
+  int32_t R;
+  int32_t ld4;
+};
+
+struct Affine {
+  float4 inv;     // 1 / (hi - lo)
+  float4 invlo;   // lo / (hi - lo)
+};
+
+__device__ __forceinline__ float4 finalize_value(const float4& yown, const float4& acc,
+                                                 float degf, float invs, const Affine& af,
+                                                 bool gather_affine) {
+  // x_own = inv * (y * deg) - inv * lo ;  b = inv * (acc * invs) - inv * lo  (or acc * invs)
+  float4 x;
+  const float ox = yown.x * degf, oy = yown.y * degf, oz = yown.z * degf, ow = yown.w * degf;
+  const float bx = acc.x * invs, by = acc.y * invs, bz = acc.z * invs, bw = acc.w * invs;
+  const float xo0 = fmaf(af.inv.x, ox, -af.invlo.x), xo1 = fmaf(af.inv.y, oy, -af.invlo.y),
+              xo2 = fmaf(af.inv.z, oz, -af.invlo.z), xo3 = fmaf(af.inv.w, ow, -af.invlo.w);
+  float g0 = bx, g1 = by, g2 = bz, g3 = bw;
+  if (gather_affine) {
+    g0 = fmaf(af.inv.x, bx, -af.invlo.x);
+    g1 = fmaf(af.inv.y, by, -af.invlo.y);
+    g2 = fmaf(af.inv.z, bz, -af.invlo.z);
+    g3 = fmaf(af.inv.w, bw, -af.invlo.w);
+  }
+  x.x = 0.5f * (xo0 + g0);
+  x.y = 0.5f * (xo1 + g1);
+  x.z = 0.5f * (xo2 + g2);
+  x.w = 0.5f * (xo3 + g3);
+  return x;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
+  constexpr int G = 32 / LPR;                       // rows per warp on the light path
+  constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
+  constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
+
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LPR - 1);
+  const int g = lane / LPR;
+  const int warp = threadIdx.x >> 5;
+  const int slab = blockIdx.y;                      // column slab of 32 float4 (R > 128 only)
+  const int c4 = slab * LPR + gl;                   // this lane's float4 column
+  const bool active = c4 < a.ld4;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
+  const int64_t nw = (int64_t)gridDim.x * kWarps;
+  const int ld4 = a.ld4;
+  const int col0 = c4 * 4;
+  const bool m0 = col0 + 0 < a.R, m1 = col0 + 1 < a.R, m2 = col0 + 2 < a.R, m3 = col0 + 3 < a.R;
+
+  Affine af;
+  af.inv = make_float4(1.f, 1.f, 1.f, 1.f);
+  af.invlo = hge_f4_zero();
+  if (a.mm_prev && active) {
+    float lo[4], inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lo[j] = 0.f;
+      inv[j] = 1.f;
+      if (col0 + j < a.R) {
+        lo[j] = hge_dec(a.mm_prev[col0 + j]);
+        const float hi = hge_dec(a.mm_prev[ld4 * 4 + col0 + j]);
+        inv[j] = 1.0f / (hi - lo[j]);
+      }
+    }
+    af.inv = make_float4(inv[0], inv[1], inv[2], inv[3]);
+    af.invlo = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
+  }
+  const bool gaff = a.gather_affine != 0;
+  const bool raw_out = a.raw_out != 0;
+
+  const float inf = __int_as_float(0x7f800000);
+  float4 vmin = make_float4(inf, inf, inf, inf);
+  float4 vmax = make_float4(-inf, -inf, -inf, -inf);
+
+  auto finish_row = [&](int row, float degf, float invs, const float4& acc) {
+    // called by the lanes that own (row, c4); acc is the full gathered sum
+    const size_t off = (size_t)row * ld4 + c4;
+    if (raw_out) {
+      a.raw[off] = acc;
+      return;
+    }
+    const float4 yown = __ldcs(a.yo + off);
+    const float4 x = finalize_value(yown, acc, degf, invs, af, gaff);
+    const float w = __frcp_rn(degf);
+    a.yo[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
+    if (m0) { vmin.x = fminf(vmin.x, x.x); vmax.x = fmaxf(vmax.x, x.x); }
+    if (m1) { vmin.y = fminf(vmin.y, x.y); vmax.y = fmaxf(vmax.y, x.y); }
+    if (m2) { vmin.z = fminf(vmin.z, x.z); vmax.z = fmaxf(vmax.z, x.z); }
+    if (m3) { vmin.w = fminf(vmin.w, x.w); vmax.w = fmaxf(vmax.w, x.w); }
+  };
+
+  // ---- long rows: one warp per chunk of the row --------------------------------------
+  for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
+    const int2 ch = a.chunks[ci];
+    const HgeHeavyRow hr = a.hrows[ch.x];
+    const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
+    const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
+    const int32_t* cidx = a.idx + start;
+    float4 acc = hge_f4_zero();
+    for (int base = 0; base < count; base += 32) {
+      const int my = (base + lane < count) ? __ldcs(cidx + base + lane) : -1;
+#pragma unroll
+      for (int r0 = 0; r0 < LPR; r0 += UR) {
+        float4 v[UR];
+#pragma unroll
+        for (int u = 0; u < UR; ++u) {
+          const int c = __shfl_sync(kFull, my, (r0 + u) * G + g);
+          v[u] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+        }
+#pragma unroll
+        for (int u = 0; u < UR; ++u) hge_f4_add(acc, v[u]);
+      }
+    }
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(kFull, acc.x, off);
+      acc.y += __shfl_xor_sync(kFull, acc.y, off);
+      acc.z += __shfl_xor_sync(kFull, acc.z, off);
+      acc.w += __shfl_xor_sync(kFull, acc.w, off);
+    }
+    if (hr.nchunks == 1) {
+      if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, acc);
+    } else {
+      if (g == 0 && active) __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
+      __threadfence();
+      __syncwarp();
+      int prev = 0;
+      if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
+      prev = __shfl_sync(kFull, prev, 0);
+      if (prev == hr.nchunks - 1) {   // this warp is the last chunk of the row to finish
+        __threadfence();
+        float4 tot = hge_f4_zero();
+        for (int k = g; k < hr.nchunks; k += G)
+          if (active) hge_f4_add(tot, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) {
+          tot.x += __shfl_xor_sync(kFull, tot.x, off);
+          tot.y += __shfl_xor_sync(kFull, tot.y, off);
+          tot.z += __shfl_xor_sync(kFull, tot.z, off);
+          tot.w += __shfl_xor_sync(kFull, tot.w, off);
+        }
+        if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, tot);
+        if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
+      }
+    }
+  }
+
+  // ---- short rows: one sub-warp of LPR lanes per row, G rows per warp -----------------
+  for (int64_t q = gw; q * G < a.n_light; q += nw) {
+    const int64_t i = q * G + g;
+    const bool valid = i < a.n_light;
+    int4 raw = make_int4(0, 0, 0, 0);
+    if (valid) raw = __ldcs(reinterpret_cast<const int4*>(a.light) + i);
+    const int row = raw.x;
+    const int deg = raw.y & 0xff;
+    const int64_t start = ((int64_t)((uint32_t)raw.y >> 8) << 32) | (uint32_t)raw.z;
+    const float invs = __int_as_float(raw.w);
+    const int32_t* ridx = a.idx + start;
+    const int maxdeg = __reduce_max_sync(kFull, deg);
+
+    int cur[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int t = k * LPR + gl;
+      cur[k] = (t < 8 && t < deg) ? __ldcs(ridx + t) : -1;
+    }
+    float4 acc = hge_f4_zero();
+    for (int base = 0; base < maxdeg; base += 8) {
+      int nxt[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int t = base + 8 + k * LPR + gl;
+        nxt[k] = (k * LPR + gl < 8 && t < deg) ? __ldcs(ridx + t) : -1;
+      }
+      float4 v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
+        v[t] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) hge_f4_add(acc, v[t]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) cur[k] = nxt[k];
+    }
+    if (valid && active) finish_row(row, (float)deg, invs, acc);
+  }
+
+  if (raw_out) return;
+
+  // ---- per-column min / max of the rows this block produced ---------------------------
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+    vmin.x = fminf(vmin.x, __shfl_xor_sync(kFull, vmin.x, off));
+    vmin.y = fminf(vmin.y, __shfl_xor_sync(kFull, vmin.y, off));
+    vmin.z = fminf(vmin.z, __shfl_xor_sync(kFull, vmin.z, off));
+    vmin.w = fminf(vmin.w, __shfl_xor_sync(kFull, vmin.w, off));
+    vmax.x = fmaxf(vmax.x, __shfl_xor_sync(kFull, vmax.x, off));
+    vmax.y = fmaxf(vmax.y, __shfl_xor_sync(kFull, vmax.y, off));
+    vmax.z = fmaxf(vmax.z, __shfl_xor_sync(kFull, vmax.z, off));
+    vmax.w = fmaxf(vmax.w, __shfl_xor_sync(kFull, vmax.w, off));
+  }
+  __shared__ float4 smin[kWarps][LPR];
+  __shared__ float4 smax[kWarps][LPR];
+  if (g == 0) {
+    smin[warp][gl] = vmin;
+    smax[warp][gl] = vmax;
+  }
+  __syncthreads();
+  if (threadIdx.x < LPR * 4) {
+    const int l = threadIdx.x >> 2, j = threadIdx.x & 3;
+    const int col = (slab * LPR + l) * 4 + j;
+    if (col < a.R) {
+      float lo = inf, hi = -inf;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        lo = fminf(lo, reinterpret_cast<const float*>(&smin[w][l])[j]);
+        hi = fmaxf(hi, reinterpret_cast<const float*>(&smax[w][l])[j]);
+      }
+      if (lo <= hi) {  // this block produced at least one row
+        atomicMin(a.mm_cur + col, hge_enc(lo));
+        atomicMax(a.mm_cur + ld4 * 4 + col, hge_enc(hi));
+      }
+    }
+  }
+}
+
+// Sharded edge half, second part: the raw sums have been all-reduced over the shards.
+__global__ void k_edge_finalize(int64_t rows, int R, int ld, const float* __restrict__ raw,
+                                const int32_t* __restrict__ deg, const float* __restrict__ invs,
+                                const int32_t* __restrict__ mm_prev, int32_t* __restrict__ mm_cur,
+                                float* __restrict__ y) {
+  // one thread per (row, column); columns are the fast index so accesses coalesce
+  __shared__ int s_min[1024], s_max[1024];
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    s_min[c] = INT32_MAX;
+    s_max[c] = INT32_MIN;
+  }
+  __syncthreads();
+  const int64_t total = rows * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = (int)(i - r * ld);
+    if (c >= R) continue;
+    const float degf = (float)deg[r];
+    float own = y[i] * degf;
+    if (mm_prev) {
+      const float lo = hge_dec(mm_prev[c]);
+      const float inv = 1.0f / (hge_dec(mm_prev[ld + c]) - lo);
+      own = fmaf(inv, own, -lo * inv);
+    }
+    const float x = 0.5f * (own + raw[i] * invs[r]);
+    y[i] = x * __frcp_rn(degf);
+    atomicMin(&s_min[c], hge_enc(x));
+    atomicMax(&s_max[c], hge_enc(x));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < R; c += blockDim.x) {
+    if (s_min[c] <= s_max[c]) {
+      atomicMin(mm_cur + c, s_min[c]);
+      atomicMax(mm_cur + ld + c, s_max[c]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side: schedule construction
+// ----------------------------------------------------------------------------------------
+
+int grid_1d(const hge_ctx* ctx, int64_t work, int block) {
+  int64_t want = (work + block - 1) / block;
+  int64_t cap = (int64_t)ctx->num_sms * 32;
+  if (want < 1) want = 1;
+  return (int)std::min(want, cap);
+}
+
+int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& h_ptr,
+                        const int64_t* d_ptr, const int32_t* d_idx, const int32_t* d_own_deg,
+                        const int32_t* d_other_deg, bool allow_empty, const char* what,
+                        HgeHalfSchedule* s) {
+  s->rows = rows;
+  s->nnz = h_ptr[rows];
+  s->ptr = d_ptr;
+  s->idx = d_idx;
+  s->chunk_sz = ctx->chunk;
+  const int light_max = ctx->light_max_deg;
+  const int chunk = ctx->chunk;
+
+  // inverse neighbour-weight sums, on the device
+  HGE_TRY(hge_dev_alloc(&s->invs, (size_t)rows));
+  k_row_invs<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
+      rows, d_ptr, d_idx, d_other_deg, s->invs);
+  HGE_CHECK_LAUNCH(ctx);
+  std::vector<float> h_invs((size_t)rows);
+  HGE_CUDA(cudaMemcpyAsync(h_invs.data(), s->invs, (size_t)rows * sizeof(float),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  (void)d_own_deg;
+
+  // counting sort of the light rows by descending degree; long rows sorted by degree too
+  std::vector<int64_t> bucket((size_t)light_max + 2, 0);
+  std::vector<std::pair<int32_t, int32_t>> heavy;  // (deg, row)
+  int32_t max_deg = 0;
+  for (int32_t r = 0; r < rows; ++r) {
+    const int64_t d = h_ptr[r + 1] - h_ptr[r];
+    if (d <= 0) {
+      if (d < 0) {
+        hge_set_error("%s row pointers decrease at row %d", what, r);
+        return HGE_ERR_INVALID;
+      }
+      if (!allow_empty) {
+        hge_set_error("%s %d has no incidence: the relaxation divides 0/0 there "
+                      "(reference: ZeroDivisionError at algebraic_distance.py:49)", what, r);
+        return HGE_ERR_EMPTY_ROW;
+      }
+    }
+    if (d > INT32_MAX) {
+      hge_set_error("%s %d has more than 2^31-1 incidences", what, r);
+      return HGE_ERR_UNSUPPORTED;
+    }
+    max_deg = std::max<int32_t>(max_deg, (int32_t)d);
+    if (d <= light_max) bucket[(size_t)d]++;
+    else heavy.emplace_back((int32_t)d, r);
+  }
+  s->max_deg = max_deg;
+  // offsets: degree light_max first ... degree 0 last
+  std::vector<int64_t> offset((size_t)light_max + 2, 0);
+  int64_t run = 0;
+  for (int d = light_max; d >= 0; --d) {
+    offset[(size_t)d] = run;
+    run += bucket[(size_t)d];
+  }
+  s->n_light = run;
+  std::vector<HgeLightItem> light((size_t)run);
+  for (int32_t r = 0; r < rows; ++r) {
+    const int64_t d = h_ptr[r + 1] - h_ptr[r];
+    if (d > light_max) continue;
+    HgeLightItem it;
+    it.row = r;
+    it.deg_hi = (uint32_t)d | (uint32_t)((h_ptr[r] >> 32) << 8);
+    it.start_lo = (uint32_t)(h_ptr[r] & 0xffffffffll);
+    it.invs = h_invs[(size_t)r];
+    light[(size_t)offset[(size_t)d]++] = it;
+  }
+  std::sort(heavy.begin(), heavy.end(), [](const std::pair<int32_t, int32_t>& x,
+                                           const std::pair<int32_t, int32_t>& y) {
+    return x.first != y.first ? x.first > y.first : x.second < y.second;
+  });
+  std::vector<HgeHeavyRow> hrows(heavy.size());
+  std::vector<int2> chunks;
+  int32_t n_partials = 0;
+  for (size_t h = 0; h < heavy.size(); ++h) {
+    HgeHeavyRow& hr = hrows[h];
+    hr.row = heavy[h].second;
+    hr.deg = heavy[h].first;
+    hr.start = h_ptr[hr.row];
+    hr.nchunks = (hr.deg + chunk - 1) / chunk;
+    hr.partial_base = 0;
+    if (hr.nchunks > 1) {
+      hr.partial_base = n_partials;
+      n_partials += hr.nchunks;
+    }
+    hr.invs = h_invs[(size_t)hr.row];
+    hr.pad = 0;
+  }
+  // chunk order: round-robin over rows sorted by size would serialise nothing; simply emit
+  // the chunks of the longest rows first so their reductions finish early.
+  for (size_t h = 0; h < heavy.size(); ++h)
+    for (int32_t c = 0; c < hrows[h].nchunks; ++c) chunks.push_back(make_int2((int)h, c));
+  s->n_hrows = (int32_t)hrows.size();
+  s->n_chunks = (int32_t)chunks.size();
+  s->n_partials = n_partials;
+
+  HGE_TRY(hge_dev_alloc(&s->light, light.size()));
+  HGE_TRY(hge_dev_alloc(&s->hrows, hrows.size()));
+  HGE_TRY(hge_dev_alloc(&s->chunks, chunks.size()));
+  if (!light.empty())
+    HGE_CUDA(cudaMemcpyAsync(s->light, light.data(), light.size() * sizeof(HgeLightItem),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  if (!hrows.empty())
+    HGE_CUDA(cudaMemcpyAsync(s->hrows, hrows.data(), hrows.size() * sizeof(HgeHeavyRow),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  if (!chunks.empty())
+    HGE_CUDA(cudaMemcpyAsync(s->chunks, chunks.data(), chunks.size() * sizeof(int2),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  HGE_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  return HGE_OK;
+}
+
+void free_half_schedule(HgeHalfSchedule* s) {
+  hge_dev_free(s->deg);
+  hge_dev_free(s->invs);
+  hge_dev_free(s->light);
+  hge_dev_free(s->hrows);
+  hge_dev_free(s->chunks);
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------
+// relaxation state
+// ----------------------------------------------------------------------------------------
+
+struct hge_algdist {
+  hge_ctx* ctx = nullptr;
+  hge_incidence* inc = nullptr;
+  int R = 0, ld = 0, ld4 = 0, lpr = 0, slabs = 1;
+  int max_iters = 0;
+  float* yn = nullptr;
+  float* ye = nullptr;
+  int32_t* mm = nullptr;        // [max_iters][2][ld]
+  float4* partials = nullptr;   // max over the two halves
+  int32_t* counters = nullptr;
+  float* stage_n = nullptr;     // host-call staging (dense [N, R] / [E, R])
+  float* stage_e = nullptr;
+  int grid = 0;
+};
+
+namespace {
+
+template <int LPR>
+int launch_half(hge_algdist* st, const HalfSweepArgs& a) {
+  dim3 grid(st->grid, st->slabs);
+  k_half_sweep<LPR><<<grid, kBlock, 0, st->ctx->stream>>>(a);
+  HGE_CHECK_LAUNCH(st->ctx);
+  return HGE_OK;
+}
+
+template <int LPR>
+int occupancy_grid(const hge_ctx* ctx, int* out) {
+  int per_sm = 0;
+  HGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_half_sweep<LPR>, kBlock, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (ctx->blocks_per_sm > 0) per_sm = ctx->blocks_per_sm;
+  *out = per_sm * ctx->num_sms;
+  return HGE_OK;
+}
+
+int run_half(hge_algdist* st, bool node_half, int sweep, float* raw) {
+  hge_incidence* inc = st->inc;
+  const HgeHalfSchedule& s = node_half ? inc->node_half : inc->edge_half;
+  HalfSweepArgs a;
+  a.idx = s.idx;
+  a.yg = reinterpret_cast<const float4*>(node_half ? st->ye : st->yn);
+  a.yo = reinterpret_cast<float4*>(node_half ? st->yn : st->ye);
+  a.light = s.light;
+  a.n_light = s.n_light;
+  a.hrows = s.hrows;
+  a.chunks = s.chunks;
+  a.n_chunks = s.n_chunks;
+  a.n_hrows = s.n_hrows;
+  a.chunk_sz = s.chunk_sz;
+  a.partials = st->partials;
+  a.counters = st->counters;
+  a.mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
+  a.mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
+  a.gather_affine = node_half ? 1 : 0;
+  a.raw_out = raw ? 1 : 0;
+  a.raw = reinterpret_cast<float4*>(raw);
+  a.R = st->R;
+  a.ld4 = st->ld4;
+  switch (st->lpr) {
+    case 1: return launch_half<1>(st, a);
+    case 2: return launch_half<2>(st, a);
+    case 4: return launch_half<4>(st, a);
+    case 8: return launch_half<8>(st, a);
+    case 16: return launch_half<16>(st, a);
+    default: return launch_half<32>(st, a);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
+                         const int64_t* n2e_ptr, const int32_t* n2e_idx,
+                         const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
+                         hge_incidence** out) {
+  HGE_REQUIRE(ctx && out, "hge_incidence_create: NULL ctx / out");
+  *out = nullptr;
+  HGE_REQUIRE(num_nodes > 0 && num_edges > 0, "hge_incidence_create: empty hypergraph (%d nodes, %d edges)",
+              num_nodes, num_edges);
+  HGE_REQUIRE(n2e_ptr && n2e_idx && e2n_ptr && e2n_idx, "hge_incidence_create: NULL CSR array");
+  HGE_REQUIRE(mem == HGE_MEM_HOST || mem == HGE_MEM_DEVICE, "hge_incidence_create: bad mem %d", mem);
+  HGE_CUDA(cudaSetDevice(ctx->device));
+
+  hge_incidence* inc = new (std::nothrow) hge_incidence();
+  if (!inc) return HGE_ERR_NOMEM;
+  inc->ctx = ctx;
+  inc->N = num_nodes;
+  inc->E = num_edges;
+  int rc = HGE_OK;
+  auto fail = [&](int code) {
+    hge_incidence_destroy(inc);
+    return code;
+  };
+
+  inc->h_n2e_ptr.resize((size_t)num_nodes + 1);
+  inc->h_e2n_ptr.resize((size_t)num_edges + 1);
+  if (mem == HGE_MEM_HOST) {
+    std::copy(n2e_ptr, n2e_ptr + num_nodes + 1, inc->h_n2e_ptr.begin());
+    std::copy(e2n_ptr, e2n_ptr + num_edges + 1, inc->h_e2n_ptr.begin());
+    const int64_t nnz_a = inc->h_n2e_ptr[num_nodes], nnz_b = inc->h_e2n_ptr[num_edges];
+    inc->owns_csr = true;
+    if ((rc = hge_dev_alloc(&inc->n2e_ptr, (size_t)num_nodes + 1)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(&inc->e2n_ptr, (size_t)num_edges + 1)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(&inc->n2e_idx, (size_t)nnz_a)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(&inc->e2n_idx, (size_t)nnz_b)) != HGE_OK) return fail(rc);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void* d, const void* h, size_t bytes) {
+      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    up(inc->n2e_ptr, n2e_ptr, ((size_t)num_nodes + 1) * 8);
+    up(inc->e2n_ptr, e2n_ptr, ((size_t)num_edges + 1) * 8);
+    up(inc->n2e_idx, n2e_idx, (size_t)nnz_a * 4);
+    up(inc->e2n_idx, e2n_idx, (size_t)nnz_b * 4);
+    if (e != cudaSuccess) {
+      hge_set_error("hge_incidence_create: upload failed: %s", cudaGetErrorString(e));
+      return fail(HGE_ERR_CUDA);
+    }
+  } else {
+    inc->owns_csr = false;
+    inc->n2e_ptr = const_cast<int64_t*>(n2e_ptr);
+    inc->e2n_ptr = const_cast<int64_t*>(e2n_ptr);
+    inc->n2e_idx = const_cast<int32_t*>(n2e_idx);
+    inc->e2n_idx = const_cast<int32_t*>(e2n_idx);
+    cudaError_t e = cudaMemcpyAsync(inc->h_n2e_ptr.data(), n2e_ptr, ((size_t)num_nodes + 1) * 8,
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(inc->h_e2n_ptr.data(), e2n_ptr, ((size_t)num_edges + 1) * 8,
+                          cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      hge_set_error("hge_incidence_create: reading row pointers failed: %s", cudaGetErrorString(e));
+      return fail(HGE_ERR_CUDA);
+    }
+  }
+  if (inc->h_n2e_ptr[0] != 0 || inc->h_e2n_ptr[0] != 0) {
+    hge_set_error("hge_incidence_create: row pointers must start at 0");
+    return fail(HGE_ERR_INVALID);
+  }
+
+  // degrees (weights are 1 / degree of the *other* side's row, algebraic_distance.py:47)
+  if ((rc = hge_dev_alloc(&inc->node_half.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(&inc->edge_half.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
+  k_row_degree<<<grid_1d(ctx, num_nodes, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, inc->n2e_ptr,
+                                                                          inc->node_half.deg);
+  ctx->launches++;
+  k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
+                                                                          inc->edge_half.deg);
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) {
+    hge_set_error("hge_incidence_create: degree kernel launch failed");
+    return fail(HGE_ERR_CUDA);
+  }
+  rc = build_half_schedule(ctx, num_nodes, inc->h_n2e_ptr, inc->n2e_ptr, inc->n2e_idx,
+                           inc->node_half.deg, inc->edge_half.deg, false, "node", &inc->node_half);
+  if (rc != HGE_OK) return fail(rc);
+  rc = build_half_schedule(ctx, num_edges, inc->h_e2n_ptr, inc->e2n_ptr, inc->e2n_idx,
+                           inc->edge_half.deg, inc->node_half.deg, false, "edge", &inc->edge_half);
+  if (rc != HGE_OK) return fail(rc);
+  *out = inc;
+  return HGE_OK;
+}
+
+int hge_incidence_destroy(hge_incidence* inc) {
+  if (!inc) return HGE_OK;
+  cudaSetDevice(inc->ctx->device);
+  cudaStreamSynchronize(inc->ctx->stream);
+  free_half_schedule(&inc->node_half);
+  free_half_schedule(&inc->edge_half);
+  if (inc->owns_csr) {
+    hge_dev_free(inc->n2e_ptr);
+    hge_dev_free(inc->n2e_idx);
+    hge_dev_free(inc->e2n_ptr);
+    hge_dev_free(inc->e2n_idx);
+  }
+  delete inc;
+  return HGE_OK;
+}
+
+int64_t hge_incidence_nnz(const hge_incidence* inc) { return inc ? inc->node_half.nnz : 0; }
+
+int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iterations,
+                       hge_algdist** out) {
+  HGE_REQUIRE(ctx && inc && out, "hge_algdist_create: NULL argument");
+  *out = nullptr;
+  HGE_REQUIRE(R >= 1 && R <= 1024, "hge_algdist_create: dimension %d not in [1, 1024]", R);
+  HGE_REQUIRE(max_iterations >= 0, "hge_algdist_create: negative iteration count");
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  hge_algdist* st = new (std::nothrow) hge_algdist();
+  if (!st) return HGE_ERR_NOMEM;
+  st->ctx = ctx;
+  st->inc = inc;
+  st->R = R;
+  st->ld = (R + 3) & ~3;
+  st->ld4 = st->ld / 4;
+  int lpr = 1;
+  while (lpr < st->ld4 && lpr < 32) lpr <<= 1;
+  st->lpr = lpr;
+  st->slabs = (st->ld4 + 31) / 32;
+  st->max_iters = max_iterations;
+  int rc = HGE_OK;
+  auto fail = [&](int code) {
+    hge_algdist_destroy(st);
+    return code;
+  };
+  if ((rc = hge_dev_alloc(&st->yn, (size_t)inc->N * st->ld)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(&st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(&st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
+    return fail(rc);
+  const size_t n_part = (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials);
+  const size_t n_cnt = (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows) * st->slabs;
+  if ((rc = hge_dev_alloc(&st->partials, n_part * st->ld4)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(&st->counters, n_cnt)) != HGE_OK) return fail(rc);
+  if (cudaMemsetAsync(st->counters, 0, std::max<size_t>(1, n_cnt) * sizeof(int32_t), ctx->stream) !=
+      cudaSuccess) {
+    hge_set_error("hge_algdist_create: memset failed");
+    return fail(HGE_ERR_CUDA);
+  }
+  switch (st->lpr) {
+    case 1: rc = occupancy_grid<1>(ctx, &st->grid); break;
+    case 2: rc = occupancy_grid<2>(ctx, &st->grid); break;
+    case 4: rc = occupancy_grid<4>(ctx, &st->grid); break;
+    case 8: rc = occupancy_grid<8>(ctx, &st->grid); break;
+    case 16: rc = occupancy_grid<16>(ctx, &st->grid); break;
+    default: rc = occupancy_grid<32>(ctx, &st->grid); break;
+  }
+  if (rc != HGE_OK) return fail(rc);
+  *out = st;
+  return HGE_OK;
+}
+
+int hge_algdist_destroy(hge_algdist* st) {
+  if (!st) return HGE_OK;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->ctx->stream);
+  hge_dev_free(st->yn);
+  hge_dev_free(st->ye);
+  hge_dev_free(st->mm);
+  hge_dev_free(st->partials);
+  hge_dev_free(st->counters);
+  hge_dev_free(st->stage_n);
+  hge_dev_free(st->stage_e);
+  delete st;
+  return HGE_OK;
+}
+
+int hge_algdist_ld(const hge_algdist* st) { return st ? st->ld : 0; }
+
+int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem) {
+  HGE_REQUIRE(st && xn && xe, "hge_algdist_load: NULL argument");
+  hge_ctx* ctx = st->ctx;
+  hge_incidence* inc = st->inc;
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  const float* dn = xn;
+  const float* de = xe;
+  if (mem == HGE_MEM_HOST) {
+    if (!st->stage_n) HGE_TRY(hge_dev_alloc(&st->stage_n, (size_t)inc->N * st->R));
+    if (!st->stage_e) HGE_TRY(hge_dev_alloc(&st->stage_e, (size_t)inc->E * st->R));
+    HGE_CUDA(cudaMemcpyAsync(st->stage_n, xn, (size_t)inc->N * st->R * 4, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    HGE_CUDA(cudaMemcpyAsync(st->stage_e, xe, (size_t)inc->E * st->R * 4, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    dn = st->stage_n;
+    de = st->stage_e;
+  }
+  k_fill_minmax<<<grid_1d(ctx, (int64_t)std::max(1, st->max_iters) * 2 * st->ld, kBlock), kBlock, 0,
+                  ctx->stream>>>(st->mm, std::max(1, st->max_iters), st->ld);
+  HGE_CHECK_LAUNCH(ctx);
+  k_load_rows<<<grid_1d(ctx, (int64_t)inc->N * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->N, st->R, st->ld, dn, inc->node_half.deg, st->yn);
+  HGE_CHECK_LAUNCH(ctx);
+  k_load_rows<<<grid_1d(ctx, (int64_t)inc->E * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->E, st->R, st->ld, de, inc->edge_half.deg, st->ye);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
+}
+
+int hge_algdist_node_half(hge_algdist* st, int sweep) {
+  HGE_REQUIRE(st && sweep >= 0 && sweep < st->max_iters, "hge_algdist_node_half: bad sweep %d", sweep);
+  HGE_CUDA(cudaSetDevice(st->ctx->device));
+  return run_half(st, true, sweep, nullptr);
+}
+
+int hge_algdist_edge_half(hge_algdist* st, int sweep) {
+  HGE_REQUIRE(st && sweep >= 0 && sweep < st->max_iters, "hge_algdist_edge_half: bad sweep %d", sweep);
+  HGE_CUDA(cudaSetDevice(st->ctx->device));
+  return run_half(st, false, sweep, nullptr);
+}
+
+int hge_algdist_edge_partial(hge_algdist* st, int sweep, float* partial) {
+  HGE_REQUIRE(st && partial && sweep >= 0 && sweep < st->max_iters,
+              "hge_algdist_edge_partial: bad argument");
+  HGE_CUDA(cudaSetDevice(st->ctx->device));
+  return run_half(st, false, sweep, partial);
+}
+
+int hge_algdist_edge_finalize(hge_algdist* st, int sweep, const float* partial,
+                              const float* inv_s_edge_global) {
+  HGE_REQUIRE(st && partial && sweep >= 0 && sweep < st->max_iters,
+              "hge_algdist_edge_finalize: bad argument");
+  HGE_REQUIRE(st->ld <= 1024, "hge_algdist_edge_finalize: dimension too large");
+  hge_ctx* ctx = st->ctx;
+  hge_incidence* inc = st->inc;
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  const int32_t* mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
+  int32_t* mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
+  const float* invs = inv_s_edge_global ? inv_s_edge_global : inc->edge_half.invs;
+  k_edge_finalize<<<grid_1d(ctx, (int64_t)inc->E * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->E, st->R, st->ld, partial, inc->edge_half.deg, invs, mm_prev, mm_cur, st->ye);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
+}
+
+int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out) {
+  HGE_REQUIRE(st && out && sweep >= 0 && sweep < std::max(1, st->max_iters),
+              "hge_algdist_minmax_ptr: bad argument");
+  *out = st->mm + (size_t)sweep * 2 * st->ld;
+  return HGE_OK;
+}
+
+int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, int mem) {
+  HGE_REQUIRE(st && xn && xe && sweeps_done >= 0 && sweeps_done <= st->max_iters,
+              "hge_algdist_store: bad argument");
+  hge_ctx* ctx = st->ctx;
+  hge_incidence* inc = st->inc;
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  const int32_t* mm = sweeps_done > 0 ? st->mm + (size_t)(sweeps_done - 1) * 2 * st->ld : nullptr;
+  float* dn = xn;
+  float* de = xe;
+  if (mem == HGE_MEM_HOST) {
+    if (!st->stage_n) HGE_TRY(hge_dev_alloc(&st->stage_n, (size_t)inc->N * st->R));
+    if (!st->stage_e) HGE_TRY(hge_dev_alloc(&st->stage_e, (size_t)inc->E * st->R));
+    dn = st->stage_n;
+    de = st->stage_e;
+  }
+  k_store_rows<<<grid_1d(ctx, (int64_t)inc->N * st->R, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->N, st->R, st->ld, st->yn, inc->node_half.deg, mm, dn);
+  HGE_CHECK_LAUNCH(ctx);
+  k_store_rows<<<grid_1d(ctx, (int64_t)inc->E * st->R, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->E, st->R, st->ld, st->ye, inc->edge_half.deg, mm, de);
+  HGE_CHECK_LAUNCH(ctx);
+  if (mem == HGE_MEM_HOST) {
+    HGE_CUDA(cudaMemcpyAsync(xn, dn, (size_t)inc->N * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaMemcpyAsync(xe, de, (size_t)inc->E * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return HGE_OK;
+}
+
+int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R, int iterations,
+                    int mem, float* lohi) {
+  HGE_REQUIRE(ctx && inc && xn && xe, "hge_algdist_run: NULL argument");
+  HGE_REQUIRE(iterations >= 0, "hge_algdist_run: negative iteration count");
+  if (iterations == 0) return HGE_OK;  // the initial vectors are the result
+  hge_algdist* st = nullptr;
+  HGE_TRY(hge_algdist_create(ctx, inc, R, iterations, &st));
+  int rc = hge_algdist_load(st, xn, xe, mem);
+  for (int t = 0; rc == HGE_OK && t < iterations; ++t) {
+    rc = hge_algdist_node_half(st, t);
+    if (rc == HGE_OK) rc = hge_algdist_edge_half(st, t);
+  }
+  if (rc == HGE_OK) rc = hge_algdist_store(st, iterations, xn, xe, mem);
+  if (rc == HGE_OK && lohi) {
+    std::vector<int32_t> h((size_t)iterations * 2 * st->ld);
+    cudaError_t e = cudaMemcpyAsync(h.data(), st->mm, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      hge_set_error("hge_algdist_run: reading min/max failed: %s", cudaGetErrorString(e));
+      rc = HGE_ERR_CUDA;
+    } else {
+      for (int t = 0; t < iterations; ++t)
+        for (int k = 0; k < 2; ++k)
+          for (int c = 0; c < R; ++c)
+            lohi[((size_t)t * 2 + k) * R + c] = hge_dec(h[((size_t)t * 2 + k) * st->ld + c]);
+    }
+  }
+  hge_algdist_destroy(st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Shared internals of libhge_b200.so: error reporting, the context object, small device
+// helpers.  Not part of the public ABI (see include/hge_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hge_b200.h"
+
+void hge_set_error(const char* fmt, ...);
+
+#define HGE_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      hge_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,              \
+                    cudaGetErrorString(e_));                                        \
+      return HGE_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define HGE_CHECK_LAUNCH(ctx)                                                       \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    HGE_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+#define HGE_REQUIRE(cond, ...)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      hge_set_error(__VA_ARGS__);                                                   \
+      return HGE_ERR_INVALID;                                                       \
+    }                                                                               \
+  } while (0)
+
+#define HGE_TRY(call)                                                               \
+  do {                                                                              \
+    int rc_ = (call);                                                               \
+    if (rc_ != HGE_OK) return rc_;                                                  \
+  } while (0)
+
+struct hge_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int num_sms;
+  // schedule tuning (hge_ctx_set_tuning)
+  int light_max_deg;
+  int chunk;
+  int blocks_per_sm;
+  int64_t launches;
+};
+
+// RAII-free device buffer helpers (everything is released explicitly by the owning object).
+template <typename T>
+static inline int hge_dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (e != cudaSuccess) {
+    hge_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+                  cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? HGE_ERR_NOMEM : HGE_ERR_CUDA;
+  }
+  return HGE_OK;
+}
+
+template <typename T>
+static inline void hge_dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+#ifdef __CUDACC__
+// Order-preserving float <-> int32 map: a < b  <=>  enc(a) < enc(b) as signed ints, so the
+// joint per-column min / max of the rescale step can be kept with atomicMin / atomicMax.
+__host__ __device__ static inline int hge_enc(float f) {
+#ifdef __CUDA_ARCH__
+  int i = __float_as_int(f);
+#else
+  int i;
+  memcpy(&i, &f, 4);
+#endif
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__host__ __device__ static inline float hge_dec(int i) {
+  i = i ^ ((i >> 31) & 0x7fffffff);
+#ifdef __CUDA_ARCH__
+  return __int_as_float(i);
+#else
+  float f;
+  memcpy(&f, &i, 4);
+  return f;
+#endif
+}
+
+__device__ __forceinline__ float4 hge_ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 hge_f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void hge_f4_add(float4& a, const float4& b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+#endif

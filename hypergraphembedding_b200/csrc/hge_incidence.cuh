@@ -1,0 +1,61 @@
+// Internal layout of the incidence object and its degree-binned gather schedule.
+//
+// One "half schedule" describes how the rows of one CSR (node->edge for the node half-sweep,
+// edge->node for the edge half-sweep) are handed to warps:
+//   * light rows (degree <= light_max_deg): one sub-warp of LPR lanes per row, rows sorted by
+//     descending degree so the sub-warps of a warp run the same trip count;
+//   * longer rows: cut into chunks of `chunk` incidences, one warp per chunk; a row with
+//     several chunks parks per-chunk partial sums and the last chunk to finish adds them in
+//     chunk order (deterministic) and finalises the row.
+#pragma once
+
+#include <vector>
+
+#include "hge_common.cuh"
+
+struct HgeLightItem {   // 16 B, read as one int4
+  int32_t row;
+  uint32_t deg_hi;      // bits 0..7 degree, bits 8..31 high bits of the CSR offset
+  uint32_t start_lo;    // low 32 bits of the CSR offset
+  float invs;           // 1 / sum of the neighbours' weights
+};
+
+struct HgeHeavyRow {    // 32 B
+  int32_t row;
+  int32_t deg;
+  int64_t start;
+  int32_t nchunks;
+  int32_t partial_base;  // first slot in the partial buffer (multi-chunk rows only)
+  float invs;
+  int32_t pad;
+};
+
+struct HgeHalfSchedule {
+  int32_t rows = 0;
+  int64_t nnz = 0;
+  const int64_t* ptr = nullptr;   // device CSR row pointers [rows + 1]
+  const int32_t* idx = nullptr;   // device CSR column ids [nnz]
+  int32_t* deg = nullptr;         // device, weight degree of each row (global degree if sharded)
+  float* invs = nullptr;          // device, 1 / sum_b (1 / deg_other[b]) per row
+  HgeLightItem* light = nullptr;
+  int64_t n_light = 0;
+  HgeHeavyRow* hrows = nullptr;
+  int32_t n_hrows = 0;
+  int2* chunks = nullptr;         // (heavy row index, chunk index)
+  int32_t n_chunks = 0;
+  int32_t n_partials = 0;
+  int32_t chunk_sz = 0;
+  int32_t max_deg = 0;
+};
+
+struct hge_incidence {
+  hge_ctx* ctx = nullptr;
+  int32_t N = 0, E = 0;
+  bool owns_csr = false;
+  int64_t* n2e_ptr = nullptr;
+  int32_t* n2e_idx = nullptr;
+  int64_t* e2n_ptr = nullptr;
+  int32_t* e2n_idx = nullptr;
+  std::vector<int64_t> h_n2e_ptr, h_e2n_ptr;
+  HgeHalfSchedule node_half, edge_half;
+};

@@ -1,0 +1,254 @@
+"""TEST INFRASTRUCTURE ONLY -- generates ``tests/golden/*.npz`` by running the
+UNMODIFIED reference (through ``oracle/ref_shim.py``) under fixed seeds.
+
+Run in the dev container, where ``/root/reference`` exists:
+
+    python -m oracle.make_golden [--only NAME]
+
+The GPU box has no reference tree; tests there read only the committed vectors.
+Each file records the numpy / scipy versions it was produced with.
+"""
+import argparse
+import hashlib
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "..", "tests", "golden")
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+from oracle import port  # noqa: E402
+from oracle.ref_shim import REFERENCE_ROOT, load_reference  # noqa: E402
+
+VERSIONS = np.array([np.__version__, scipy.__version__])
+
+
+def incidence_pairs(hg):
+  """(node_id, edge_id) pairs in node-map iteration order, then edge.nodes order
+  is re-derivable because the fixtures are consistent (checked below)."""
+  n2e = [(n, e) for n, d in hg.node.items() for e in d.edges]
+  e2n = {(n, e) for e, d in hg.edge.items() for n in d.nodes}
+  assert set(n2e) == e2n, "fixture node->edges and edge->nodes disagree"
+  return np.asarray(n2e, dtype=np.int64)
+
+
+def hash_columns(arrays, keys):
+  h = hashlib.sha256()
+  for k in keys:
+    h.update(np.ascontiguousarray(arrays[k], dtype=np.int64).tobytes())
+  return h.hexdigest()
+
+
+INDEX_KEYS = ("left_node", "left_edge", "right_node", "right_edge")
+NEIGH_KEYS = ("neigh_node", "neigh_edge")
+
+
+def emb_to_arrays(emb, n, e, r):
+  xn = np.zeros((n, r), np.float32)
+  xe = np.zeros((e, r), np.float32)
+  for i, v in emb.node.items():
+    xn[i] = v.values
+  for i, v in emb.edge.items():
+    xe[i] = v.values
+  return xn, xe
+
+
+def arrays_to_emb(ref, xn, xe, method="AlgebraicDistance"):
+  emb = ref.HypergraphEmbedding()
+  emb.dim = xn.shape[1]
+  emb.method_name = method
+  for i in range(xn.shape[0]):
+    emb.node[i].values.extend(xn[i])
+  for i in range(xe.shape[0]):
+    emb.edge[i].values.extend(xe[i])
+  return emb
+
+
+def graphs(ref):
+  U = ref.hypergraph_util
+  tiny = ref.Hypergraph()
+  for n, e in [(0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2)]:
+    U.AddNodeToEdge(tiny, n, e)  # tests/test_embedding.py:14-22
+  random.seed(2024)
+  rand25 = U.CreateRandomHyperGraph(25, 25, 0.25)  # tests/test_embedding.py:58
+  youtube = ref.Hypergraph()
+  with open(os.path.join(REFERENCE_ROOT, "test_data",
+                         "snap_youtube_tiny.hypergraph.pb"), "rb") as f:
+    youtube.ParseFromString(f.read())
+  return {"tiny": tiny, "rand25": rand25, "youtube": youtube}
+
+
+def save(name, **kw):
+  path = os.path.join(GOLDEN, name + ".npz")
+  np.savez_compressed(path, versions=VERSIONS, **kw)
+  print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024.0))
+
+
+def gen_algdist(ref, name, hg, dim, iters, seed):
+  U = ref.hypergraph_util
+  np.random.seed(seed)
+  t = time.time()
+  emb = ref.algebraic_distance.EmbedAlgebraicDistance(
+      hg, dim, iterations=iters, run_in_parallel=True, disable_pbar=True)
+  dt = time.time() - t
+  state = np.random.get_state()
+  node_ids = sorted(hg.node)
+  edge_ids = sorted(hg.edge)
+  xn = np.stack([np.asarray(emb.node[i].values, np.float32) for i in node_ids])
+  xe = np.stack([np.asarray(emb.edge[i].values, np.float32) for i in edge_ids])
+  save("algdist_" + name, pairs=incidence_pairs(hg), dim=dim, iters=iters,
+       seed=seed, xn=xn, xe=xe, node_ids=np.asarray(node_ids),
+       edge_ids=np.asarray(edge_ids), rng_pos=state[2],
+       rng_key_sha=hashlib.sha256(state[1].tobytes()).hexdigest(),
+       method_name=emb.method_name, ref_seconds=dt)
+  return xn, xe
+
+
+def compressed(ref, hg):
+  return ref.hypergraph_util.CompressRange(hg)[0]
+
+
+def csr_parts(m):
+  m = m.tocsr()
+  m.sort_indices()
+  return dict(indptr=m.indptr, indices=m.indices, data=m.data,
+              shape=np.asarray(m.shape))
+
+
+def gen_weights(ref, name, hg, xn, xe, same_type):
+  hc = compressed(ref, hg)
+  emb = arrays_to_emb(ref, xn, xe)
+  W = ref.hg2v_weighting
+  out = dict(pairs=incidence_pairs(hc), xn=xn, xe=xe)
+  for alpha in (0, 0.3):
+    a, b = W.WeightByDistance(hc, alpha, emb, np.linalg.norm, True)
+    for tag, m in (("n2e", a), ("e2n", b)):
+      for k, v in csr_parts(m).items():
+        out["wbd_a%s_%s_%s" % (alpha, tag, k)] = v
+    if same_type:
+      a, b = W.WeightBySameTypeDistance(hc, alpha, emb, np.linalg.norm, True)
+      for tag, m in (("n2n", a), ("e2e", b)):
+        for k, v in csr_parts(m).items():
+          out["wbstd_a%s_%s_%s" % (alpha, tag, k)] = v
+  ns, es = W.ComputeSpans(hc, emb, run_in_parallel=False, disable_pbar=True)
+  out["node_span"] = np.asarray([ns[i] for i in range(xn.shape[0])])
+  out["edge_span"] = np.asarray([es[i] for i in range(xe.shape[0])])
+  for alpha in (0, 0.3):
+    a, b = W.WeightByNeighborhood(hc, alpha)
+    for tag, m in (("n2e", a), ("e2n", b)):
+      for k, v in csr_parts(m).items():
+        out["wbn_a%s_%s_%s" % (alpha, tag, k)] = v
+  save("weights_" + name, **out)
+
+
+def gen_boolean(ref, name, hg, k, num_samples, neg, seed, full):
+  hc = compressed(ref, hg)
+  np.random.seed(seed)
+  recs = ref.hg2v_sample.BooleanSamples(hc, k, num_samples, neg_samples=neg,
+                                        disable_pbar=True)
+  state = np.random.get_state()
+  arr = port.records_to_arrays(recs, k)
+  out = dict(pairs=incidence_pairs(hc), k=k, num_samples=num_samples, neg=neg,
+             seed=seed, node_rows=np.asarray(list(hc.node)),
+             edge_rows=np.asarray(list(hc.edge)), count=len(recs),
+             rng_pos=state[2],
+             rng_key_sha=hashlib.sha256(state[1].tobytes()).hexdigest(),
+             index_sha=hash_columns(arr, INDEX_KEYS),
+             neigh_sha=hash_columns(arr, NEIGH_KEYS))
+  if full:
+    for key, v in arr.items():
+      out["col_" + key] = v.astype(np.float32) if "prob" in key else v.astype(
+          np.int32)
+  save("boolean_" + name, **out)
+
+
+def gen_hobe(ref, name, hg, xn, xe, k, num_samples, seed, parallel, stride):
+  hc = compressed(ref, hg)
+  emb = arrays_to_emb(ref, xn, xe)
+  np.random.seed(seed)
+  t = time.time()
+  recs = ref.hg2v_sample.AlgebraicDistanceSamples(
+      hc, emb, k, num_samples, run_in_parallel=parallel, disable_pbar=True)
+  dt = time.time() - t
+  state = np.random.get_state()
+  arr = port.records_to_arrays(recs, k)
+  out = dict(pairs=incidence_pairs(hc), xn=xn, xe=xe, k=k,
+             num_samples=num_samples, seed=seed, count=len(recs),
+             node_rows=np.asarray(list(hc.node)),
+             edge_rows=np.asarray(list(hc.edge)), rng_pos=state[2],
+             rng_key_sha=hashlib.sha256(state[1].tobytes()).hexdigest(),
+             index_sha=hash_columns(arr, INDEX_KEYS), ref_seconds=dt,
+             neighbours_deterministic=not parallel, stride=stride)
+  if not parallel:
+    out["neigh_sha"] = hash_columns(arr, NEIGH_KEYS)
+  prob = np.where(~np.isnan(arr["nn_prob"]), arr["nn_prob"],
+                  np.where(~np.isnan(arr["ee_prob"]), arr["ee_prob"],
+                           arr["ne_prob"])).astype(np.float32)
+  if stride == 1:
+    for key, v in arr.items():
+      if "prob" in key:
+        out["col_" + key] = v.astype(np.float32)
+      elif parallel and key in NEIGH_KEYS:
+        continue
+      else:
+        out["col_" + key] = v.astype(np.int32)
+  else:
+    out["prob_strided"] = prob[::stride]
+    kind = np.where(~np.isnan(arr["nn_prob"]), 0,
+                    np.where(~np.isnan(arr["ee_prob"]), 1, 2)).astype(np.int8)
+    out["kind_counts"] = np.bincount(kind, minlength=3)
+  save("hobe_" + name, **out)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--only", default=None)
+  args = ap.parse_args()
+  os.makedirs(GOLDEN, exist_ok=True)
+  ref = load_reference()
+  g = graphs(ref)
+
+  def want(n):
+    return args.only is None or args.only == n
+
+  cfg = {"tiny": (3, 5, 1), "rand25": (5, 10, 2), "youtube": (10, 20, 0)}
+  embs = {}
+  for name, (dim, iters, seed) in cfg.items():
+    path = os.path.join(GOLDEN, "algdist_%s.npz" % name)
+    if want("algdist") or not os.path.exists(path):
+      embs[name] = gen_algdist(ref, name, g[name], dim, iters, seed)
+    else:
+      z = np.load(path)
+      embs[name] = (z["xn"], z["xe"])
+  if want("weights"):
+    gen_weights(ref, "tiny", g["tiny"], *embs["tiny"], same_type=True)
+    gen_weights(ref, "rand25", g["rand25"], *embs["rand25"], same_type=True)
+    gen_weights(ref, "youtube", g["youtube"], *embs["youtube"], same_type=False)
+  if want("boolean"):
+    gen_boolean(ref, "tiny", g["tiny"], 2, 3, 2, 5, full=True)
+    gen_boolean(ref, "rand25", g["rand25"], 4, 6, 3, 6, full=True)
+    gen_boolean(ref, "youtube_s10", g["youtube"], 5, 10, 0, 7, full=True)
+    gen_boolean(ref, "youtube_s200", g["youtube"], 5, 200, 0, 7, full=False)
+    gen_boolean(ref, "youtube_s200_neg", g["youtube"], 5, 200, 50, 8, full=False)
+  if want("hobe"):
+    gen_hobe(ref, "tiny", g["tiny"], *embs["tiny"], k=2, num_samples=3, seed=9,
+             parallel=False, stride=1)
+    gen_hobe(ref, "rand25", g["rand25"], *embs["rand25"], k=3, num_samples=5,
+             seed=10, parallel=False, stride=1)
+    gen_hobe(ref, "youtube_s2", g["youtube"], *embs["youtube"], k=5,
+             num_samples=2, seed=11, parallel=False, stride=1)
+  if want("hobe_full"):
+    # BASELINE.json configs[0]: defaults of embedding.py:389-397.  Pair sets and
+    # probabilities are deterministic with run_in_parallel=True; neighbour
+    # draws are not and are not recorded.
+    gen_hobe(ref, "youtube_s200", g["youtube"], *embs["youtube"], k=5,
+             num_samples=200, seed=0, parallel=True, stride=8)
+
+
+if __name__ == "__main__":
+  main()

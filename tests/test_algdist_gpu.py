@@ -1,0 +1,170 @@
+"""Parity of the CUDA relaxation (through the C ABI) with the reference / the oracle port.
+
+Bar (BASELINE.json north_star): incidence distances within 1e-5 relative of the reference's
+numpy result from the same initial vectors; the reference computes in f64 and stores fp32,
+the kernels compute in fp32.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from conftest import (csr_from_pairs, embedding_arrays, hypergraph_from_pairs, incidence_distances,
+                      load_golden)
+
+pytestmark = pytest.mark.gpu
+
+RTOL_DIST = 1e-5      # relative, on per-incidence L2 distances (north star)
+ATOL_COORD = 2e-5     # absolute, on coordinates in [0, 1]
+
+
+def assert_distance_parity(A, xn, xe, ref_xn, ref_xe, rtol=RTOL_DIST):
+  d = incidence_distances(A, xn, xe)
+  dr = incidence_distances(A, ref_xn, ref_xe)
+  scale = max(dr.max(), 1e-30)
+  # relative to the distance itself, with a floor of 1% of the largest distance so that
+  # near-coincident pairs are judged on the scale of the embedding
+  err = np.abs(d - dr) / np.maximum(dr, 1e-2 * scale)
+  assert err.max() <= rtol, "max relative distance error %.3g" % err.max()
+  assert np.abs(np.asarray(xn, np.float64) - ref_xn).max() <= ATOL_COORD
+  assert np.abs(np.asarray(xe, np.float64) - ref_xe).max() <= ATOL_COORD
+
+
+@pytest.mark.parametrize("name", ["tiny", "rand25", "youtube"])
+def test_embed_algebraic_distance_matches_reference_golden(name):
+  from hypergraphembedding_b200 import EmbedAlgebraicDistance
+  g = load_golden("algdist_" + name)
+  hg = hypergraph_from_pairs(g["pairs"])
+  np.random.seed(int(g["seed"]))
+  emb = EmbedAlgebraicDistance(hg, int(g["dim"]), iterations=int(g["iters"]), run_in_parallel=False,
+                               disable_pbar=True)
+  assert emb.dim == int(g["dim"])
+  assert emb.method_name == "AlgebraicDistance"          # algebraic_distance.py:168
+  assert sorted(emb.node) == g["node_ids"].tolist()
+  assert sorted(emb.edge) == g["edge_ids"].tolist()
+  xn, xe = embedding_arrays(emb, g["node_ids"], g["edge_ids"])
+  r = np.searchsorted(g["node_ids"], g["pairs"][:, 0])
+  c = np.searchsorted(g["edge_ids"], g["pairs"][:, 1])
+  A = csr_from_pairs(np.stack([r, c], 1), shape=(len(g["node_ids"]), len(g["edge_ids"])))
+  assert_distance_parity(A, xn, xe, g["xn"], g["xe"])
+  # the call consumed the global RNG exactly as the reference does
+  assert int(np.random.get_state()[2]) == int(g["rng_pos"])
+
+
+def _run(A, xn0, xe0, iters, gpu_ctx, lohi=None, device=False):
+  from hypergraphembedding_b200 import algebraic_distance as ad
+  inc = ad.make_incidence(A, ctx=gpu_ctx)
+  try:
+    if device:
+      import torch
+      xn = torch.from_numpy(xn0.copy()).cuda()
+      xe = torch.from_numpy(xe0.copy()).cuda()
+      ad.relax(inc, xn, xe, iters, lohi=lohi)
+      torch.cuda.synchronize()
+      return xn.cpu().numpy(), xe.cpu().numpy()
+    xn, xe = xn0.copy(), xe0.copy()
+    ad.relax(inc, xn, xe, iters, lohi=lohi)
+    return xn, xe
+  finally:
+    inc.close()
+
+
+def _random_graph(rng, n, e, nnz):
+  rows = rng.integers(0, n, nnz)
+  cols = rng.integers(0, e, nnz)
+  rows = np.concatenate([rows, np.arange(n), rng.integers(0, n, e)])
+  cols = np.concatenate([cols, rng.integers(0, e, n), np.arange(e)])
+  return csr_from_pairs(np.stack([rows, cols], 1), shape=(n, e))
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 8, 10, 16, 31, 32, 33, 64, 100, 128, 130, 200])
+def test_all_dimensions_against_oracle(R, gpu_ctx):
+  from oracle import port
+  rng = np.random.default_rng(R)
+  A = _random_graph(rng, 700, 90, 3000)
+  xn0 = rng.random((700, R)).astype(np.float32)
+  xe0 = rng.random((90, R)).astype(np.float32)
+  ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, 6)
+  xn, xe = _run(A, xn0, xe0, 6, gpu_ctx)
+  assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_long_rows_and_device_pointers(device, gpu_ctx):
+  """Rows that take the multi-chunk path (degree >> chunk) on both sides, plus min/max log."""
+  from oracle import port
+  rng = np.random.default_rng(5)
+  n, e = 6000, 300
+  rows = np.concatenate([np.arange(n), np.arange(n), rng.integers(0, n, 20000), np.zeros(e, int),
+                         np.ones(e, int)])
+  cols = np.concatenate([np.zeros(n, int), rng.integers(0, e, n), rng.integers(0, e, 20000),
+                         np.arange(e), np.arange(e)])
+  A = csr_from_pairs(np.stack([rows, cols], 1), shape=(n, e))   # edge 0 holds every node
+  R = 32
+  xn0 = rng.random((n, R)).astype(np.float32)
+  xe0 = rng.random((e, R)).astype(np.float32)
+  iters = 8
+  ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, iters)
+  lohi = np.zeros((iters, 2, R), np.float32)
+  xn, xe = _run(A, xn0, xe0, iters, gpu_ctx, lohi=lohi, device=device)
+  assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
+  assert np.all(lohi[:, 0] < lohi[:, 1])
+  # after the rescale every column spans [0, 1] exactly (joint over nodes and edges)
+  both = np.concatenate([xn, xe])
+  assert np.allclose(both.min(0), 0, atol=1e-6) and np.allclose(both.max(0), 1, atol=1e-6)
+
+
+def test_tuning_knobs_do_not_change_results(gpu_ctx):
+  rng = np.random.default_rng(11)
+  A = _random_graph(rng, 3000, 200, 40000)
+  xn0 = rng.random((3000, 32)).astype(np.float32)
+  xe0 = rng.random((200, 32)).astype(np.float32)
+  base = _run(A, xn0, xe0, 5, gpu_ctx)
+  try:
+    for light, chunk in ((8, 32), (255, 1024), (1, 64)):
+      gpu_ctx.set_tuning(light, chunk, 2)
+      xn, xe = _run(A, xn0, xe0, 5, gpu_ctx)
+      assert np.abs(xn - base[0]).max() < 1e-5 and np.abs(xe - base[1]).max() < 1e-5
+  finally:
+    gpu_ctx.set_tuning(64, 256, 0)
+
+
+def test_results_are_reproducible_run_to_run(gpu_ctx):
+  rng = np.random.default_rng(12)
+  A = _random_graph(rng, 5000, 100, 60000)
+  xn0 = rng.random((5000, 32)).astype(np.float32)
+  xe0 = rng.random((100, 32)).astype(np.float32)
+  a = _run(A, xn0, xe0, 10, gpu_ctx)
+  b = _run(A, xn0, xe0, 10, gpu_ctx)
+  assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_zero_iterations_returns_the_initial_vectors(gpu_ctx):
+  rng = np.random.default_rng(1)
+  A = _random_graph(rng, 50, 10, 100)
+  xn0 = rng.random((50, 7)).astype(np.float32)
+  xe0 = rng.random((10, 7)).astype(np.float32)
+  xn, xe = _run(A, xn0, xe0, 0, gpu_ctx)
+  assert np.array_equal(xn, xn0) and np.array_equal(xe, xe0)
+
+
+def test_isolated_edge_raises_like_the_reference():
+  """An edge key without members: the reference divides 0/0 (algebraic_distance.py:49)."""
+  from hypergraphembedding_b200 import EmbedAlgebraicDistance, Hypergraph
+  hg = Hypergraph()
+  hg.node[0].edges.extend([0])
+  hg.node[1].edges.extend([0])
+  hg.edge[0].nodes.extend([0, 1])
+  hg.edge[1].weight = 1.0      # present, but nobody is in it
+  with pytest.raises(ZeroDivisionError):
+    EmbedAlgebraicDistance(hg, 2, iterations=1, disable_pbar=True)
+
+
+def test_config2_scale_properties(gpu_ctx):
+  """BASELINE.json configs[1] shape at 1/10 size against the oracle, full size by properties."""
+  from hypergraphembedding_b200 import synthetic
+  from oracle import port
+  A = synthetic.power_law_hypergraph(100000, 50000, 1000000, seed=7)
+  xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], 32, seed=3)
+  ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, 20)
+  xn, xe = _run(A, xn0, xe0, 20, gpu_ctx)
+  assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
