@@ -252,6 +252,7 @@ def run_ours(args, spec):
       evs[2 * t + 2].record()
     torch.cuda.synchronize()
     half_ms.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(2 * sweeps))
+  st.store(sweeps, xn, xe)
   st.close()
   half_ms = np.asarray(half_ms)
   node_ms = float(half_ms[0::2].mean())

@@ -128,31 +128,45 @@ struct Affine {
   float4 invlo;   // lo / (hi - lo)
 };
 
+// x' = (x_own + b) / 2 with x_own = inv (y deg) - inv lo and b = inv (acc invs) - inv lo (node
+// half) or b = acc invs (edge half), folded into two FMAs per component:
+//     x' = c1 y + (c2 acc + c3),  c1 = inv deg / 2,  c2 = inv invs / 2 | invs / 2,
+//     c3 = -inv lo | -inv lo / 2.   (the halvings are exact)
 __device__ __forceinline__ float4 finalize_value(const float4& yown, const float4& acc,
                                                  float degf, float invs, const Affine& af,
                                                  bool gather_affine) {
-  // x_own = inv * (y * deg) - inv * lo ;  b = inv * (acc * invs) - inv * lo  (or acc * invs)
+  const float hd = 0.5f * degf, hs = 0.5f * invs;
   float4 x;
-  const float ox = yown.x * degf, oy = yown.y * degf, oz = yown.z * degf, ow = yown.w * degf;
-  const float bx = acc.x * invs, by = acc.y * invs, bz = acc.z * invs, bw = acc.w * invs;
-  const float xo0 = fmaf(af.inv.x, ox, -af.invlo.x), xo1 = fmaf(af.inv.y, oy, -af.invlo.y),
-              xo2 = fmaf(af.inv.z, oz, -af.invlo.z), xo3 = fmaf(af.inv.w, ow, -af.invlo.w);
-  float g0 = bx, g1 = by, g2 = bz, g3 = bw;
   if (gather_affine) {
-    g0 = fmaf(af.inv.x, bx, -af.invlo.x);
-    g1 = fmaf(af.inv.y, by, -af.invlo.y);
-    g2 = fmaf(af.inv.z, bz, -af.invlo.z);
-    g3 = fmaf(af.inv.w, bw, -af.invlo.w);
+    x.x = fmaf(af.inv.x * hd, yown.x, fmaf(af.inv.x * hs, acc.x, -af.invlo.x));
+    x.y = fmaf(af.inv.y * hd, yown.y, fmaf(af.inv.y * hs, acc.y, -af.invlo.y));
+    x.z = fmaf(af.inv.z * hd, yown.z, fmaf(af.inv.z * hs, acc.z, -af.invlo.z));
+    x.w = fmaf(af.inv.w * hd, yown.w, fmaf(af.inv.w * hs, acc.w, -af.invlo.w));
+  } else {
+    x.x = fmaf(af.inv.x * hd, yown.x, fmaf(hs, acc.x, -0.5f * af.invlo.x));
+    x.y = fmaf(af.inv.y * hd, yown.y, fmaf(hs, acc.y, -0.5f * af.invlo.y));
+    x.z = fmaf(af.inv.z * hd, yown.z, fmaf(hs, acc.z, -0.5f * af.invlo.z));
+    x.w = fmaf(af.inv.w * hd, yown.w, fmaf(hs, acc.w, -0.5f * af.invlo.w));
   }
-  x.x = 0.5f * (xo0 + g0);
-  x.y = 0.5f * (xo1 + g1);
-  x.z = 0.5f * (xo2 + g2);
-  x.w = 0.5f * (xo3 + g3);
   return x;
 }
 
+// Compensated (Kahan) accumulation: a row can have 10^5..10^6 incidences and the relaxation
+// renormalises every sweep, so plain fp32 running sums are the dominant error term against the
+// reference's f64 arithmetic (measured on the youtube fixture: 2e-5 vs 1e-6 absolute).
+__device__ __forceinline__ void kahan_add(float4& s, float4& c, const float4& v) {
+  float y, t;
+  y = v.x - c.x; t = s.x + y; c.x = (t - s.x) - y; s.x = t;
+  y = v.y - c.y; t = s.y + y; c.y = (t - s.y) - y; s.y = t;
+  y = v.z - c.z; t = s.z + y; c.z = (t - s.z) - y; s.z = t;
+  y = v.w - c.w; t = s.w + y; c.w = (t - s.w) - y; s.w = t;
+}
+__device__ __forceinline__ float4 kahan_result(const float4& s, const float4& c) {
+  return make_float4(s.x - c.x, s.y - c.y, s.z - c.z, s.w - c.w);
+}
+
 template <int LPR>
-__global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
+__global__ void __launch_bounds__(kBlock, 3) k_half_sweep(const HalfSweepArgs a) {
   constexpr int G = 32 / LPR;                       // rows per warp on the light path
   constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
   constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
@@ -219,7 +233,7 @@ __global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
     const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
     const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
     const int32_t* cidx = a.idx + start;
-    float4 acc = hge_f4_zero();
+    float4 acc = hge_f4_zero(), comp = hge_f4_zero();
     for (int base = 0; base < count; base += 32) {
       const int my = (base + lane < count) ? __ldcs(cidx + base + lane) : -1;
 #pragma unroll
@@ -231,9 +245,10 @@ __global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
           v[u] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
         }
 #pragma unroll
-        for (int u = 0; u < UR; ++u) hge_f4_add(acc, v[u]);
+        for (int u = 0; u < UR; ++u) kahan_add(acc, comp, v[u]);
       }
     }
+    acc = kahan_result(acc, comp);
 #pragma unroll
     for (int off = LPR; off < 32; off <<= 1) {
       acc.x += __shfl_xor_sync(kFull, acc.x, off);
@@ -252,9 +267,11 @@ __global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
       prev = __shfl_sync(kFull, prev, 0);
       if (prev == hr.nchunks - 1) {   // this warp is the last chunk of the row to finish
         __threadfence();
-        float4 tot = hge_f4_zero();
+        float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
         for (int k = g; k < hr.nchunks; k += G)
-          if (active) hge_f4_add(tot, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+          if (active)
+            kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+        tot = kahan_result(tot, tcomp);
 #pragma unroll
         for (int off = LPR; off < 32; off <<= 1) {
           tot.x += __shfl_xor_sync(kFull, tot.x, off);
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
       const int t = k * LPR + gl;
       cur[k] = (t < 8 && t < deg) ? __ldcs(ridx + t) : -1;
     }
-    float4 acc = hge_f4_zero();
+    float4 acc = hge_f4_zero(), comp = hge_f4_zero();
     for (int base = 0; base < maxdeg; base += 8) {
       int nxt[K];
 #pragma unroll
@@ -302,11 +319,11 @@ __global__ void __launch_bounds__(kBlock) k_half_sweep(const HalfSweepArgs a) {
         v[t] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) hge_f4_add(acc, v[t]);
+      for (int t = 0; t < 8; ++t) kahan_add(acc, comp, v[t]);
 #pragma unroll
       for (int k = 0; k < K; ++k) cur[k] = nxt[k];
     }
-    if (valid && active) finish_row(row, (float)deg, invs, acc);
+    if (valid && active) finish_row(row, (float)deg, invs, kahan_result(acc, comp));
   }
 
   if (raw_out) return;
@@ -411,7 +428,7 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
   const int chunk = ctx->chunk;
 
   // inverse neighbour-weight sums, on the device
-  HGE_TRY(hge_dev_alloc(&s->invs, (size_t)rows));
+  HGE_TRY(hge_dev_alloc(ctx, &s->invs, (size_t)rows));
   k_row_invs<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
       rows, d_ptr, d_idx, d_other_deg, s->invs);
   HGE_CHECK_LAUNCH(ctx);
@@ -495,9 +512,9 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
   s->n_chunks = (int32_t)chunks.size();
   s->n_partials = n_partials;
 
-  HGE_TRY(hge_dev_alloc(&s->light, light.size()));
-  HGE_TRY(hge_dev_alloc(&s->hrows, hrows.size()));
-  HGE_TRY(hge_dev_alloc(&s->chunks, chunks.size()));
+  HGE_TRY(hge_dev_alloc(ctx, &s->light, light.size()));
+  HGE_TRY(hge_dev_alloc(ctx, &s->hrows, hrows.size()));
+  HGE_TRY(hge_dev_alloc(ctx, &s->chunks, chunks.size()));
   if (!light.empty())
     HGE_CUDA(cudaMemcpyAsync(s->light, light.data(), light.size() * sizeof(HgeLightItem),
                              cudaMemcpyHostToDevice, ctx->stream));
@@ -511,12 +528,12 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
   return HGE_OK;
 }
 
-void free_half_schedule(HgeHalfSchedule* s) {
-  hge_dev_free(s->deg);
-  hge_dev_free(s->invs);
-  hge_dev_free(s->light);
-  hge_dev_free(s->hrows);
-  hge_dev_free(s->chunks);
+void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s) {
+  hge_dev_free(ctx, s->deg);
+  hge_dev_free(ctx, s->invs);
+  hge_dev_free(ctx, s->light);
+  hge_dev_free(ctx, s->hrows);
+  hge_dev_free(ctx, s->chunks);
 }
 
 }  // namespace
@@ -627,10 +644,10 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
     std::copy(e2n_ptr, e2n_ptr + num_edges + 1, inc->h_e2n_ptr.begin());
     const int64_t nnz_a = inc->h_n2e_ptr[num_nodes], nnz_b = inc->h_e2n_ptr[num_edges];
     inc->owns_csr = true;
-    if ((rc = hge_dev_alloc(&inc->n2e_ptr, (size_t)num_nodes + 1)) != HGE_OK) return fail(rc);
-    if ((rc = hge_dev_alloc(&inc->e2n_ptr, (size_t)num_edges + 1)) != HGE_OK) return fail(rc);
-    if ((rc = hge_dev_alloc(&inc->n2e_idx, (size_t)nnz_a)) != HGE_OK) return fail(rc);
-    if ((rc = hge_dev_alloc(&inc->e2n_idx, (size_t)nnz_b)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(ctx, &inc->n2e_ptr, (size_t)num_nodes + 1)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(ctx, &inc->e2n_ptr, (size_t)num_edges + 1)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(ctx, &inc->n2e_idx, (size_t)nnz_a)) != HGE_OK) return fail(rc);
+    if ((rc = hge_dev_alloc(ctx, &inc->e2n_idx, (size_t)nnz_b)) != HGE_OK) return fail(rc);
     cudaError_t e = cudaSuccess;
     auto up = [&](void* d, const void* h, size_t bytes) {
       if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -666,8 +683,8 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
   }
 
   // degrees (weights are 1 / degree of the *other* side's row, algebraic_distance.py:47)
-  if ((rc = hge_dev_alloc(&inc->node_half.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(&inc->edge_half.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &inc->node_half.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &inc->edge_half.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
   k_row_degree<<<grid_1d(ctx, num_nodes, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, inc->n2e_ptr,
                                                                           inc->node_half.deg);
   ctx->launches++;
@@ -691,14 +708,16 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
 int hge_incidence_destroy(hge_incidence* inc) {
   if (!inc) return HGE_OK;
   cudaSetDevice(inc->ctx->device);
-  cudaStreamSynchronize(inc->ctx->stream);
-  free_half_schedule(&inc->node_half);
-  free_half_schedule(&inc->edge_half);
+  hge_algdist_destroy(inc->cached);
+  inc->cached = nullptr;
+  const hge_ctx* ctx = inc->ctx;
+  free_half_schedule(ctx, &inc->node_half);
+  free_half_schedule(ctx, &inc->edge_half);
   if (inc->owns_csr) {
-    hge_dev_free(inc->n2e_ptr);
-    hge_dev_free(inc->n2e_idx);
-    hge_dev_free(inc->e2n_ptr);
-    hge_dev_free(inc->e2n_idx);
+    hge_dev_free(ctx, inc->n2e_ptr);
+    hge_dev_free(ctx, inc->n2e_idx);
+    hge_dev_free(ctx, inc->e2n_ptr);
+    hge_dev_free(ctx, inc->e2n_idx);
   }
   delete inc;
   return HGE_OK;
@@ -730,14 +749,14 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
     hge_algdist_destroy(st);
     return code;
   };
-  if ((rc = hge_dev_alloc(&st->yn, (size_t)inc->N * st->ld)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(&st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(&st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
+  if ((rc = hge_dev_alloc(ctx, &st->yn, (size_t)inc->N * st->ld)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
     return fail(rc);
   const size_t n_part = (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials);
   const size_t n_cnt = (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows) * st->slabs;
-  if ((rc = hge_dev_alloc(&st->partials, n_part * st->ld4)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(&st->counters, n_cnt)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &st->partials, n_part * st->ld4)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &st->counters, n_cnt)) != HGE_OK) return fail(rc);
   if (cudaMemsetAsync(st->counters, 0, std::max<size_t>(1, n_cnt) * sizeof(int32_t), ctx->stream) !=
       cudaSuccess) {
     hge_set_error("hge_algdist_create: memset failed");
@@ -759,14 +778,14 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
 int hge_algdist_destroy(hge_algdist* st) {
   if (!st) return HGE_OK;
   cudaSetDevice(st->ctx->device);
-  cudaStreamSynchronize(st->ctx->stream);
-  hge_dev_free(st->yn);
-  hge_dev_free(st->ye);
-  hge_dev_free(st->mm);
-  hge_dev_free(st->partials);
-  hge_dev_free(st->counters);
-  hge_dev_free(st->stage_n);
-  hge_dev_free(st->stage_e);
+  const hge_ctx* ctx = st->ctx;
+  hge_dev_free(ctx, st->yn);
+  hge_dev_free(ctx, st->ye);
+  hge_dev_free(ctx, st->mm);
+  hge_dev_free(ctx, st->partials);
+  hge_dev_free(ctx, st->counters);
+  hge_dev_free(ctx, st->stage_n);
+  hge_dev_free(ctx, st->stage_e);
   delete st;
   return HGE_OK;
 }
@@ -781,8 +800,8 @@ int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem)
   const float* dn = xn;
   const float* de = xe;
   if (mem == HGE_MEM_HOST) {
-    if (!st->stage_n) HGE_TRY(hge_dev_alloc(&st->stage_n, (size_t)inc->N * st->R));
-    if (!st->stage_e) HGE_TRY(hge_dev_alloc(&st->stage_e, (size_t)inc->E * st->R));
+    if (!st->stage_n) HGE_TRY(hge_dev_alloc(ctx, &st->stage_n, (size_t)inc->N * st->R));
+    if (!st->stage_e) HGE_TRY(hge_dev_alloc(ctx, &st->stage_e, (size_t)inc->E * st->R));
     HGE_CUDA(cudaMemcpyAsync(st->stage_n, xn, (size_t)inc->N * st->R * 4, cudaMemcpyHostToDevice,
                              ctx->stream));
     HGE_CUDA(cudaMemcpyAsync(st->stage_e, xe, (size_t)inc->E * st->R * 4, cudaMemcpyHostToDevice,
@@ -855,8 +874,8 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
   float* dn = xn;
   float* de = xe;
   if (mem == HGE_MEM_HOST) {
-    if (!st->stage_n) HGE_TRY(hge_dev_alloc(&st->stage_n, (size_t)inc->N * st->R));
-    if (!st->stage_e) HGE_TRY(hge_dev_alloc(&st->stage_e, (size_t)inc->E * st->R));
+    if (!st->stage_n) HGE_TRY(hge_dev_alloc(ctx, &st->stage_n, (size_t)inc->N * st->R));
+    if (!st->stage_e) HGE_TRY(hge_dev_alloc(ctx, &st->stage_e, (size_t)inc->E * st->R));
     dn = st->stage_n;
     de = st->stage_e;
   }
@@ -879,8 +898,14 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
   HGE_REQUIRE(ctx && inc && xn && xe, "hge_algdist_run: NULL argument");
   HGE_REQUIRE(iterations >= 0, "hge_algdist_run: negative iteration count");
   if (iterations == 0) return HGE_OK;  // the initial vectors are the result
-  hge_algdist* st = nullptr;
-  HGE_TRY(hge_algdist_create(ctx, inc, R, iterations, &st));
+  // the workspace (Y rows, min/max slots, partial sums) is kept with the incidence and re-used
+  hge_algdist* st = inc->cached;
+  if (!st || st->R != R || st->max_iters < iterations || st->ctx != ctx) {
+    hge_algdist_destroy(inc->cached);
+    inc->cached = nullptr;
+    HGE_TRY(hge_algdist_create(ctx, inc, R, iterations, &st));
+    inc->cached = st;
+  }
   int rc = hge_algdist_load(st, xn, xe, mem);
   for (int t = 0; rc == HGE_OK && t < iterations; ++t) {
     rc = hge_algdist_node_half(st, t);
@@ -901,7 +926,6 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
             lohi[((size_t)t * 2 + k) * R + c] = hge_dec(h[((size_t)t * 2 + k) * st->ld + c]);
     }
   }
-  hge_algdist_destroy(st);
   return rc;
 }
 

@@ -53,23 +53,27 @@ struct hge_ctx {
   int64_t launches;
 };
 
-// RAII-free device buffer helpers (everything is released explicitly by the owning object).
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the
+// context's stream; hge_ctx_create raises the pool's release threshold so freed blocks are
+// reused instead of being returned to the driver).  Everything is released explicitly by the
+// owning object; all work of a context is queued on one stream, so stream order is enough.
 template <typename T>
-static inline int hge_dev_alloc(T** p, size_t count) {
+static inline int hge_dev_alloc(const hge_ctx* ctx, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), count * sizeof(T), ctx->stream);
   if (e != cudaSuccess) {
-    hge_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+    hge_set_error("cudaMallocAsync of %zu bytes failed: %s", count * sizeof(T),
                   cudaGetErrorString(e));
+    cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? HGE_ERR_NOMEM : HGE_ERR_CUDA;
   }
   return HGE_OK;
 }
 
 template <typename T>
-static inline void hge_dev_free(T*& p) {
-  if (p) cudaFree(p);
+static inline void hge_dev_free(const hge_ctx* ctx, T*& p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
   p = nullptr;
 }
 

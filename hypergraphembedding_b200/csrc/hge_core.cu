@@ -53,6 +53,13 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   // NULL selects the legacy default stream, which is also torch's default stream, so work
   // queued by the caller on that stream is ordered with ours.
   ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+  // keep freed blocks in the stream-ordered pool: the per-call workspaces are re-used
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  cudaGetLastError();
   *out = ctx;
   return HGE_OK;
 }
@@ -67,7 +74,13 @@ int hge_ctx_destroy(hge_ctx* ctx) {
 
 int hge_ctx_set_stream(hge_ctx* ctx, void* stream) {
   HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_stream: ctx is NULL");
-  ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t next = reinterpret_cast<cudaStream_t>(stream);
+  if (next != ctx->stream) {
+    // allocations and frees are ordered on the context's stream: drain it before switching
+    HGE_CUDA(cudaSetDevice(ctx->device));
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->stream = next;
   return HGE_OK;
 }
 

@@ -58,4 +58,5 @@ struct hge_incidence {
   int32_t* e2n_idx = nullptr;
   std::vector<int64_t> h_n2e_ptr, h_e2n_ptr;
   HgeHalfSchedule node_half, edge_half;
+  hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls
 };

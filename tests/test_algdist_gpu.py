@@ -13,20 +13,30 @@ from conftest import (csr_from_pairs, embedding_arrays, hypergraph_from_pairs, i
 
 pytestmark = pytest.mark.gpu
 
-RTOL_DIST = 1e-5      # relative, on per-incidence L2 distances (north star)
-ATOL_COORD = 2e-5     # absolute, on coordinates in [0, 1]
+RTOL = 1e-5          # north star: distances and weights within 1e-5 relative, fp32
+ATOL_WEIGHT = 1e-6   # absolute slack on HOBE weights in [0, 1] (they reach exactly 0)
 
 
-def assert_distance_parity(A, xn, xe, ref_xn, ref_xe, rtol=RTOL_DIST):
+def assert_distance_parity(A, xn, xe, ref_xn, ref_xe):
+  """|d - d_ref| <= 1e-5 d_ref + 1e-6 sqrt(R) on every incidence distance, and the same bound
+  on the HOBE weight w = (sqrt(R) - d) / sqrt(R) (hg2v_sample.py:537-541):
+  |w - w_ref| <= 1e-5 |w_ref| + 1e-6.
+
+  A purely relative bound is undefined for coincident pairs: the reference stores fp32, and
+  that rounding alone moves its own smallest fixture distance (6.5e-7) by 9%.  The absolute
+  term is 1e-6 in weight units, i.e. 1e-6 sqrt(R) in distance units (~16 ulp of a unit-range
+  fp32 coordinate)."""
+  R = np.asarray(ref_xn).shape[1]
   d = incidence_distances(A, xn, xe)
   dr = incidence_distances(A, ref_xn, ref_xe)
-  scale = max(dr.max(), 1e-30)
-  # relative to the distance itself, with a floor of 1% of the largest distance so that
-  # near-coincident pairs are judged on the scale of the embedding
-  err = np.abs(d - dr) / np.maximum(dr, 1e-2 * scale)
-  assert err.max() <= rtol, "max relative distance error %.3g" % err.max()
-  assert np.abs(np.asarray(xn, np.float64) - ref_xn).max() <= ATOL_COORD
-  assert np.abs(np.asarray(xe, np.float64) - ref_xe).max() <= ATOL_COORD
+  bound = RTOL * dr + ATOL_WEIGHT * np.sqrt(R)
+  worst = (np.abs(d - dr) / bound).max()
+  assert worst <= 1.0, "distance error is %.2f x the allowed bound" % worst
+  w = (np.sqrt(R) - d) / np.sqrt(R)
+  wr = (np.sqrt(R) - dr) / np.sqrt(R)
+  worst_w = (np.abs(w - wr) / (RTOL * np.abs(wr) + ATOL_WEIGHT)).max()
+  assert worst_w <= 1.0, "weight error is %.2f x the allowed bound" % worst_w
+  return worst, worst_w
 
 
 @pytest.mark.parametrize("name", ["tiny", "rand25", "youtube"])
@@ -123,7 +133,7 @@ def test_tuning_knobs_do_not_change_results(gpu_ctx):
     for light, chunk in ((8, 32), (255, 1024), (1, 64)):
       gpu_ctx.set_tuning(light, chunk, 2)
       xn, xe = _run(A, xn0, xe0, 5, gpu_ctx)
-      assert np.abs(xn - base[0]).max() < 1e-5 and np.abs(xe - base[1]).max() < 1e-5
+      assert np.abs(xn - base[0]).max() < 2e-6 and np.abs(xe - base[1]).max() < 2e-6
   finally:
     gpu_ctx.set_tuning(64, 256, 0)
 
