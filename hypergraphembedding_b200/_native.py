@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libhge_b200.so")
+# HGE_LIB_PATH selects an experimental build of the same library (tools/sweep_variants.py)
+LIB_PATH = os.environ.get("HGE_LIB_PATH") or os.path.join(_PKG_DIR, "libhge_b200.so")
 
 HGE_OK = 0
 HGE_ERR_INVALID = -1
@@ -68,6 +69,29 @@ SIGNATURES = {
     "hge_algdist_minmax_ptr": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "hge_algdist_ld": (ctypes.c_int, [c_vp]),
     "hge_algdist_store": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int]),
+    "hge_incidence_l2": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, c_vp, ctypes.c_int]),
+    "hge_pair_l2": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int,
+                                   c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int]),
+    "hge_scale_transform": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_double, c_vp,
+                                           ctypes.c_int]),
+    "hge_row_span": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp,
+                                    ctypes.c_int]),
+    "hge_same_type_prob": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp,
+                                          ctypes.c_int64, c_vp, ctypes.c_int]),
+    "hge_diff_type_prob": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp,
+                                          ctypes.c_int]),
+    "hge_mt19937_random_raw": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp]),
+    "hge_mt19937_interval": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_int64, c_vp]),
+    "hge_spgemm_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                       ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int64,
+                                       ctypes.c_int, c_vp, c_vp, ctypes.c_int64]),
+    "hge_sample_adj_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int64,
+                                           c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp,
+                                           ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "hge_sample_neighbors": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64,
+                                            ctypes.c_int, c_vp, c_vp, c_vp]),
 }
 
 
@@ -217,12 +241,17 @@ class Incidence(object):
                                        MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)),
           "hge_incidence_create")
     self.handle = handle
+    self.nnz_n2e = int(keep[1].shape[0])
+    self.nnz_e2n = int(keep[3].shape[0])
     if not device:
       self._keep = None  # the library copied the arrays
 
   @property
   def nnz(self):
     return int(self.ctx.lib.hge_incidence_nnz(self.handle))
+
+  def nnz_of(self, order):
+    return self.nnz_n2e if order == 0 else self.nnz_e2n
 
   def close(self):
     if getattr(self, "handle", None):
@@ -298,3 +327,181 @@ class AlgDistState(object):
       self.close()
     except Exception:
       pass
+
+
+# ---------------------------------------------------------------------------------------------
+# distances / weights / probabilities
+# ---------------------------------------------------------------------------------------------
+
+
+def _mem(*arrays):
+  dev = [is_device(a) for a in arrays if a is not None]
+  assert all(dev) or not any(dev), "mixing host and device arrays in one call"
+  return MEM_DEVICE if dev and dev[0] else MEM_HOST
+
+
+def _f32(a):
+  if is_device(a):
+    return a
+  return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _new_like(ref, n, dtype=np.float32):
+  if is_device(ref):
+    import torch
+    return torch.empty(int(n), dtype=torch.float32 if dtype == np.float32 else torch.int32,
+                       device=ref.device)
+  return np.empty(int(n), dtype=dtype)
+
+
+def incidence_l2(ctx, inc, xn, xe, order=0, as_weight=False, nnz=None):
+  """Per-incidence L2 distance (or HOBE weight) in node->edge (order 0) / edge->node (1) order."""
+  xn, xe = _f32(xn), _f32(xe)
+  R = int(xn.shape[1])
+  out = _new_like(xn, inc.nnz_of(order) if nnz is None else nnz)
+  check(ctx.lib.hge_incidence_l2(ctx.handle, inc.handle, ptr(xn), ptr(xe), R, int(order),
+                                 1 if as_weight else 0, ptr(out), _mem(xn, xe)), "hge_incidence_l2")
+  return out
+
+
+def pair_l2(ctx, xa, xb, ia, ib):
+  xa, xb = _f32(xa), _f32(xb)
+  if not is_device(ia):
+    ia, ib = _as_i32(ia), _as_i32(ib)
+  n = int(ia.shape[0])
+  out = _new_like(xa, n)
+  check(ctx.lib.hge_pair_l2(ctx.handle, ptr(xa), int(xa.shape[0]), ptr(xb), int(xb.shape[0]),
+                            int(xa.shape[1]), ptr(ia), ptr(ib), n, ptr(out), _mem(xa, xb, ia, ib)),
+        "hge_pair_l2")
+  return out
+
+
+def scale_transform(ctx, values, alpha, want_minmax=False):
+  """In place alpha + (1 - alpha) * (1 - zero_one(values)); asserts 0 <= alpha <= 1."""
+  mm = np.zeros(2, dtype=np.float32) if want_minmax else None
+  check(ctx.lib.hge_scale_transform(ctx.handle, ptr(values), int(values.shape[0]), float(alpha),
+                                    ptr(mm), _mem(values)), "hge_scale_transform")
+  return (values, mm) if want_minmax else values
+
+
+def row_span(ctx, inc, xn, xe, side):
+  xn, xe = _f32(xn), _f32(xe)
+  out = _new_like(xn, inc.num_nodes if side == 0 else inc.num_edges)
+  check(ctx.lib.hge_row_span(ctx.handle, inc.handle, ptr(xn), ptr(xe), int(xn.shape[1]), int(side),
+                             ptr(out), _mem(xn, xe)), "hge_row_span")
+  return out
+
+
+def same_type_prob(ctx, inc, side, w, pi, pj):
+  if not is_device(pi):
+    pi, pj = _as_i32(pi), _as_i32(pj)
+  out = _new_like(w, int(pi.shape[0]))
+  check(ctx.lib.hge_same_type_prob(ctx.handle, inc.handle, int(side), ptr(w), ptr(pi), ptr(pj),
+                                   int(pi.shape[0]), ptr(out), _mem(w, pi, pj)), "hge_same_type_prob")
+  return out
+
+
+def diff_type_prob(ctx, inc, w_e2n, pn, pe):
+  if not is_device(pn):
+    pn, pe = _as_i32(pn), _as_i32(pe)
+  out = _new_like(w_e2n, int(pn.shape[0]))
+  check(ctx.lib.hge_diff_type_prob(ctx.handle, inc.handle, ptr(w_e2n), ptr(pn), ptr(pe),
+                                   int(pn.shape[0]), ptr(out), _mem(w_e2n, pn, pe)),
+        "hge_diff_type_prob")
+  return out
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side sampling (numpy legacy RNG replay)
+# ---------------------------------------------------------------------------------------------
+
+
+class LegacyRngState(object):
+  """The process-global numpy RandomState as the 625-word buffer the library advances."""
+
+  def __init__(self):
+    st = np.random.get_state()
+    assert st[0] == "MT19937"
+    self._rest = (st[3], st[4])
+    self.buf = np.empty(625, dtype=np.uint32)
+    self.buf[:624] = st[1]
+    self.buf[624] = st[2]
+
+  def copy(self):
+    other = LegacyRngState.__new__(LegacyRngState)
+    other._rest = self._rest
+    other.buf = self.buf.copy()
+    return other
+
+  def commit(self):
+    """Writes the advanced state back so later np.random calls continue the same stream."""
+    np.random.set_state(("MT19937", self.buf[:624].copy(), int(self.buf[624])) + self._rest)
+
+
+class CsrArrays(object):
+  """(int64 ptr, int32 idx, shape) of a canonical boolean CSR on the host."""
+
+  def __init__(self, matrix):
+    import scipy.sparse as sps
+    m = sps.csr_matrix(matrix)
+    self.shape = m.shape
+    self.ptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    self.idx = np.ascontiguousarray(m.indices, dtype=np.int32)
+
+
+def _factors(mats):
+  args = []
+  for m in list(mats) + [None] * (3 - len(mats)):
+    args += [ptr(m.ptr) if m is not None else None, ptr(m.idx) if m is not None else None]
+  kind = len(mats) - 1
+  mid_cols = mats[1].shape[1] if kind >= 1 else 0
+  out_cols = mats[-1].shape[1]
+  return kind, args, int(mid_cols), int(out_cols)
+
+
+def spgemm_rows(mats, rows, sorted_rows=False):
+  """Rows of mats[0] (* mats[1] (* mats[2])) in scipy's stored order (or sorted)."""
+  lib = load_library()
+  kind, args, mid_cols, out_cols = _factors(mats)
+  rows = _as_i32(rows)
+  out_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
+  check(lib.hge_spgemm_rows(kind, *args, mid_cols, out_cols, ptr(rows), len(rows),
+                            1 if sorted_rows else 0, ptr(out_ptr), None, 0), "hge_spgemm_rows")
+  out_idx = np.empty(int(out_ptr[-1]), dtype=np.int32)
+  check(lib.hge_spgemm_rows(kind, *args, mid_cols, out_cols, ptr(rows), len(rows),
+                            1 if sorted_rows else 0, ptr(out_ptr), ptr(out_idx), len(out_idx)),
+        "hge_spgemm_rows")
+  return out_ptr, out_idx
+
+
+def sample_adj_rows(mats, rows, samples_per_row, state, replace=False, negative=False):
+  """_sample_adj_matrix over mats[0] (* mats[1] (* mats[2])): returns (row, col) int32 arrays."""
+  lib = load_library()
+  kind, args, mid_cols, out_cols = _factors(mats)
+  rows = _as_i32(rows)
+  samples = _as_i32(samples_per_row)
+  assert len(samples) == len(rows)
+  assert len(samples) > 0
+  cap = int(samples.astype(np.int64).sum())
+  out_row = np.empty(cap, dtype=np.int32)
+  out_col = np.empty(cap, dtype=np.int32)
+  count = ctypes.c_int64(0)
+  check(lib.hge_sample_adj_rows(kind, *args, mid_cols, out_cols, ptr(rows), len(rows), ptr(samples),
+                                1 if replace else 0, 1 if negative else 0, ptr(state.buf),
+                                ptr(out_row), ptr(out_col), cap, ctypes.byref(count)),
+        "hge_sample_adj_rows")
+  return out_row[:count.value], out_col[:count.value]
+
+
+def sample_neighbors(n2e, e2n, nodes, edges, k, state):
+  lib = load_library()
+  nodes, edges = _as_i32(nodes), _as_i32(edges)
+  m = len(nodes)
+  nbr_e = np.empty((m, k), dtype=np.int32)
+  nbr_n = np.empty((m, k), dtype=np.int32)
+  rc = lib.hge_sample_neighbors(ptr(n2e.ptr), ptr(n2e.idx), ptr(e2n.ptr), ptr(e2n.idx), ptr(nodes),
+                                ptr(edges), m, int(k), ptr(state.buf), ptr(nbr_e), ptr(nbr_n))
+  if rc == HGE_ERR_INVALID and "cannot be empty" in last_error():
+    raise ValueError("'a' cannot be empty unless no samples are taken")
+  check(rc, "hge_sample_neighbors")
+  return nbr_e, nbr_n

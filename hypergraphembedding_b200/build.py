@@ -41,26 +41,28 @@ def needs_build():
   return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
-  """Compiles every CUDA / C++ source under csrc/ into one shared library."""
-  if not force and not needs_build():
-    return LIB_PATH
+def build(force=False, verbose=False, defines=(), out=None, tag=""):
+  """Compiles every CUDA / C++ source under csrc/ into one shared library.  `defines`, `out`
+  and `tag` build an experimental variant (tools/sweep_variants.py) next to the default."""
+  out = out or LIB_PATH
+  if not defines and not force and not needs_build():
+    return out
   nvcc = find_nvcc()
   objs = []
-  obj_dir = os.path.join(PKG_DIR, "csrc", "_obj")
+  obj_dir = os.path.join(PKG_DIR, "csrc", "_obj" + tag)
   os.makedirs(obj_dir, exist_ok=True)
   procs = []
   for src in sources():
     obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
     objs.append(obj)
-    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c", src, "-o", obj]
     procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                         text=True)))
   log = []
   failed = False
   for src, p in procs:
-    out, _ = p.communicate()
-    log.append("== %s\n%s" % (os.path.basename(src), out))
+    text, _ = p.communicate()
+    log.append("== %s\n%s" % (os.path.basename(src), text))
     failed |= p.returncode != 0
   with open(os.path.join(obj_dir, "build.log"), "w") as f:
     f.write("\n".join(log))
@@ -68,11 +70,11 @@ def build(force=False, verbose=False):
     sys.stderr.write("\n".join(log) + "\n")
   if failed:
     raise RuntimeError("nvcc failed; see the log above")
-  tmp = LIB_PATH + ".tmp"
+  tmp = out + ".tmp"
   subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-gencode",
                                                                "arch=compute_100a,code=sm_100a"])
-  os.replace(tmp, LIB_PATH)
-  return LIB_PATH
+  os.replace(tmp, out)
+  return out
 
 
 if __name__ == "__main__":

@@ -165,8 +165,41 @@ __device__ __forceinline__ float4 kahan_result(const float4& s, const float4& c)
   return make_float4(s.x - c.x, s.y - c.y, s.z - c.z, s.w - c.w);
 }
 
+// Adds n gathered rows to a compensated accumulator.  HGE_ACCUM_MODE selects how:
+//   0  plain running sum per lane (default).  A lane never adds more than chunk / G values in a
+//      row before the per-lane sums are combined pairwise across the sub-warps and the chunk
+//      sums are combined with compensation, so the blocked sum is already as accurate as the
+//      compensated ones: on the youtube fixture (an edge of 2 217 members) all three modes
+//      land at 1.0-1.1e-6 absolute distance error against the f64 reference
+//      (profiles/r1_variant_sweep.md).
+//   1  pairwise tree over the n values, then one compensated add of the block sum
+//   2  one compensated add per value
+#ifndef HGE_ACCUM_MODE
+#define HGE_ACCUM_MODE 0
+#endif
+template <int N>
+__device__ __forceinline__ void accumulate(float4& s, float4& c, float4 (&v)[N]) {
+#if HGE_ACCUM_MODE == 0
+#pragma unroll
+  for (int t = 0; t < N; ++t) hge_f4_add(s, v[t]);
+#elif HGE_ACCUM_MODE == 2
+#pragma unroll
+  for (int t = 0; t < N; ++t) kahan_add(s, c, v[t]);
+#else
+#pragma unroll
+  for (int stride = 1; stride < N; stride <<= 1) {
+#pragma unroll
+    for (int t = 0; t + stride < N; t += 2 * stride) hge_f4_add(v[t], v[t + stride]);
+  }
+  kahan_add(s, c, v[0]);
+#endif
+}
+
 template <int LPR>
-__global__ void __launch_bounds__(kBlock, 3) k_half_sweep(const HalfSweepArgs a) {
+#ifndef HGE_MIN_BLOCKS
+#define HGE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const HalfSweepArgs a) {
   constexpr int G = 32 / LPR;                       // rows per warp on the light path
   constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
   constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
@@ -209,14 +242,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_half_sweep(const HalfSweepArgs a)
   float4 vmin = make_float4(inf, inf, inf, inf);
   float4 vmax = make_float4(-inf, -inf, -inf, -inf);
 
-  auto finish_row = [&](int row, float degf, float invs, const float4& acc) {
+  auto finish_row = [&](int row, float degf, float invs, const float4& yown, const float4& acc) {
     // called by the lanes that own (row, c4); acc is the full gathered sum
     const size_t off = (size_t)row * ld4 + c4;
     if (raw_out) {
       a.raw[off] = acc;
       return;
     }
-    const float4 yown = __ldcs(a.yo + off);
     const float4 x = finalize_value(yown, acc, degf, invs, af, gaff);
     const float w = __frcp_rn(degf);
     a.yo[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
@@ -227,103 +259,152 @@ __global__ void __launch_bounds__(kBlock, 3) k_half_sweep(const HalfSweepArgs a)
   };
 
   // ---- long rows: one warp per chunk of the row --------------------------------------
-  for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
-    const int2 ch = a.chunks[ci];
-    const HgeHeavyRow hr = a.hrows[ch.x];
-    const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
-    const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
-    const int32_t* cidx = a.idx + start;
-    float4 acc = hge_f4_zero(), comp = hge_f4_zero();
-    for (int base = 0; base < count; base += 32) {
-      const int my = (base + lane < count) ? __ldcs(cidx + base + lane) : -1;
+  // Loads are software-pipelined: the descriptor of the next chunk and the next block of 32
+  // column ids are requested before the current block's rows are consumed, so a warp pays
+  // one memory latency per block of 32 gathered rows.
+  {
+    int2 ch_next = make_int2(0, 0);
+    if (gw < a.n_chunks) ch_next = __ldcs(a.chunks + gw);
+    for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
+      const int2 ch = ch_next;
+      if (ci + nw < a.n_chunks) ch_next = __ldcs(a.chunks + ci + nw);
+      const HgeHeavyRow hr = a.hrows[ch.x];
+      const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
+      const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
+      const int32_t* cidx = a.idx + start;
+      const bool single = hr.nchunks == 1;
+      float4 yown = hge_f4_zero();
+      if (single && g == 0 && active && !raw_out) yown = __ldcs(a.yo + (size_t)hr.row * ld4 + c4);
+      float4 acc = hge_f4_zero(), comp = hge_f4_zero();
+      int my = (lane < count) ? __ldcs(cidx + lane) : -1;
+      for (int base = 0; base < count; base += 32) {
+        const int my_next = (base + 32 + lane < count) ? __ldcs(cidx + base + 32 + lane) : -1;
 #pragma unroll
-      for (int r0 = 0; r0 < LPR; r0 += UR) {
-        float4 v[UR];
+        for (int r0 = 0; r0 < LPR; r0 += UR) {
+          float4 v[UR];
 #pragma unroll
-        for (int u = 0; u < UR; ++u) {
-          const int c = __shfl_sync(kFull, my, (r0 + u) * G + g);
-          v[u] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+          for (int u = 0; u < UR; ++u) {
+            const int c = __shfl_sync(kFull, my, (r0 + u) * G + g);
+            v[u] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+          }
+          accumulate<UR>(acc, comp, v);
         }
-#pragma unroll
-        for (int u = 0; u < UR; ++u) kahan_add(acc, comp, v[u]);
+        my = my_next;
       }
-    }
-    acc = kahan_result(acc, comp);
+      acc = kahan_result(acc, comp);
 #pragma unroll
-    for (int off = LPR; off < 32; off <<= 1) {
-      acc.x += __shfl_xor_sync(kFull, acc.x, off);
-      acc.y += __shfl_xor_sync(kFull, acc.y, off);
-      acc.z += __shfl_xor_sync(kFull, acc.z, off);
-      acc.w += __shfl_xor_sync(kFull, acc.w, off);
-    }
-    if (hr.nchunks == 1) {
-      if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, acc);
-    } else {
-      if (g == 0 && active) __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
-      __threadfence();
-      __syncwarp();
-      int prev = 0;
-      if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
-      prev = __shfl_sync(kFull, prev, 0);
-      if (prev == hr.nchunks - 1) {   // this warp is the last chunk of the row to finish
+      for (int off = LPR; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(kFull, acc.x, off);
+        acc.y += __shfl_xor_sync(kFull, acc.y, off);
+        acc.z += __shfl_xor_sync(kFull, acc.z, off);
+        acc.w += __shfl_xor_sync(kFull, acc.w, off);
+      }
+      if (single) {
+        if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, acc);
+      } else {
+        if (g == 0 && active)
+          __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
         __threadfence();
-        float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
-        for (int k = g; k < hr.nchunks; k += G)
-          if (active)
-            kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
-        tot = kahan_result(tot, tcomp);
+        __syncwarp();
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
+        prev = __shfl_sync(kFull, prev, 0);
+        if (prev == hr.nchunks - 1) {   // this warp is the last chunk of the row to finish
+          __threadfence();
+          if (g == 0 && active && !raw_out) yown = __ldcs(a.yo + (size_t)hr.row * ld4 + c4);
+          float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
+          for (int k = g; k < hr.nchunks; k += G)
+            if (active)
+              kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+          tot = kahan_result(tot, tcomp);
 #pragma unroll
-        for (int off = LPR; off < 32; off <<= 1) {
-          tot.x += __shfl_xor_sync(kFull, tot.x, off);
-          tot.y += __shfl_xor_sync(kFull, tot.y, off);
-          tot.z += __shfl_xor_sync(kFull, tot.z, off);
-          tot.w += __shfl_xor_sync(kFull, tot.w, off);
+          for (int off = LPR; off < 32; off <<= 1) {
+            tot.x += __shfl_xor_sync(kFull, tot.x, off);
+            tot.y += __shfl_xor_sync(kFull, tot.y, off);
+            tot.z += __shfl_xor_sync(kFull, tot.z, off);
+            tot.w += __shfl_xor_sync(kFull, tot.w, off);
+          }
+          if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, tot);
+          if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
         }
-        if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, tot);
-        if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
       }
     }
   }
 
   // ---- short rows: one sub-warp of LPR lanes per row, G rows per warp -----------------
-  for (int64_t q = gw; q * G < a.n_light; q += nw) {
-    const int64_t i = q * G + g;
-    const bool valid = i < a.n_light;
-    int4 raw = make_int4(0, 0, 0, 0);
-    if (valid) raw = __ldcs(reinterpret_cast<const int4*>(a.light) + i);
-    const int row = raw.x;
-    const int deg = raw.y & 0xff;
-    const int64_t start = ((int64_t)((uint32_t)raw.y >> 8) << 32) | (uint32_t)raw.z;
-    const float invs = __int_as_float(raw.w);
-    const int32_t* ridx = a.idx + start;
-    const int maxdeg = __reduce_max_sync(kFull, deg);
-
+  // Two-deep software pipeline over the row descriptors: while the rows of quad q are being
+  // gathered, the descriptor of quad q+2 and the first 8 column ids of quad q+1 are already
+  // in flight, so a quad of short rows costs one memory latency instead of four.
+  {
+    const int4* light4 = reinterpret_cast<const int4*>(a.light);
+    auto load_item = [&](int64_t q) -> int4 {
+      const int64_t i = q * G + g;
+      return (i < a.n_light) ? __ldcs(light4 + i) : make_int4(-1, 0, 0, 0);
+    };
+    auto item_idx = [&](const int4& it) -> const int32_t* {
+      return a.idx + (((int64_t)((uint32_t)it.y >> 8) << 32) | (uint32_t)it.z);
+    };
+    int4 it0 = load_item(gw);
+    int4 it1 = load_item(gw + nw);
     int cur[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int t = k * LPR + gl;
-      cur[k] = (t < 8 && t < deg) ? __ldcs(ridx + t) : -1;
-    }
-    float4 acc = hge_f4_zero(), comp = hge_f4_zero();
-    for (int base = 0; base < maxdeg; base += 8) {
-      int nxt[K];
+    {
+      const int32_t* ridx = item_idx(it0);
+      const int deg = it0.y & 0xff;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const int t = base + 8 + k * LPR + gl;
-        nxt[k] = (k * LPR + gl < 8 && t < deg) ? __ldcs(ridx + t) : -1;
+        const int t = k * LPR + gl;
+        cur[k] = (t < 8 && t < deg) ? __ldcs(ridx + t) : -1;
       }
-      float4 v[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
-        v[t] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) kahan_add(acc, comp, v[t]);
-#pragma unroll
-      for (int k = 0; k < K; ++k) cur[k] = nxt[k];
     }
-    if (valid && active) finish_row(row, (float)deg, invs, kahan_result(acc, comp));
+    for (int64_t q = gw; q * G < a.n_light; q += nw) {
+      const int4 it2 = load_item(q + 2 * nw);
+      int first1[K];
+      {
+        const int32_t* ridx1 = item_idx(it1);
+        const int deg1 = it1.y & 0xff;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int t = k * LPR + gl;
+          first1[k] = (t < 8 && t < deg1) ? __ldcs(ridx1 + t) : -1;
+        }
+      }
+      const int row = it0.x;
+      const bool valid = row >= 0;
+      const int deg = it0.y & 0xff;
+      const float invs = __int_as_float(it0.w);
+      const int32_t* ridx = item_idx(it0);
+      const int maxdeg = __reduce_max_sync(kFull, deg);
+      float4 yown = hge_f4_zero();
+      if (valid && active && !raw_out) yown = __ldcs(a.yo + (size_t)row * ld4 + c4);
+
+      float4 acc = hge_f4_zero(), comp = hge_f4_zero();
+      for (int base = 0; base < maxdeg; base += 8) {
+        int nxt[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int t = base + 8 + k * LPR + gl;
+          nxt[k] = (k * LPR + gl < 8 && t < deg) ? __ldcs(ridx + t) : -1;
+        }
+        float4 v[8];
+        const int live = maxdeg - base;   // warp-uniform: rows are sorted by degree, so the
+#pragma unroll                            // slots past the longest row of the quad are skipped
+        for (int t = 0; t < 8; ++t) {
+          v[t] = hge_f4_zero();
+          if (t < live) {
+            const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
+            if (c >= 0 && active) v[t] = __ldg(a.yg + (size_t)c * ld4 + c4);
+          }
+        }
+        accumulate<8>(acc, comp, v);
+#pragma unroll
+        for (int k = 0; k < K; ++k) cur[k] = nxt[k];
+      }
+      if (valid && active) finish_row(row, (float)deg, invs, yown, kahan_result(acc, comp));
+      it0 = it1;
+      it1 = it2;
+#pragma unroll
+      for (int k = 0; k < K; ++k) cur[k] = first1[k];
+    }
   }
 
   if (raw_out) return;
@@ -449,11 +530,8 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
         hge_set_error("%s row pointers decrease at row %d", what, r);
         return HGE_ERR_INVALID;
       }
-      if (!allow_empty) {
-        hge_set_error("%s %d has no incidence: the relaxation divides 0/0 there "
-                      "(reference: ZeroDivisionError at algebraic_distance.py:49)", what, r);
-        return HGE_ERR_EMPTY_ROW;
-      }
+      if (s->first_empty < 0) s->first_empty = r;
+      (void)allow_empty;
     }
     if (d > INT32_MAX) {
       hge_set_error("%s %d has more than 2^31-1 incidences", what, r);
@@ -731,6 +809,14 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   *out = nullptr;
   HGE_REQUIRE(R >= 1 && R <= 1024, "hge_algdist_create: dimension %d not in [1, 1024]", R);
   HGE_REQUIRE(max_iterations >= 0, "hge_algdist_create: negative iteration count");
+  if (inc->node_half.first_empty >= 0 || inc->edge_half.first_empty >= 0) {
+    const bool node = inc->node_half.first_empty >= 0;
+    hge_set_error("%s %d has no incidence: the relaxation divides 0/0 there "
+                  "(reference: ZeroDivisionError at algebraic_distance.py:49)",
+                  node ? "node" : "edge",
+                  node ? inc->node_half.first_empty : inc->edge_half.first_empty);
+    return HGE_ERR_EMPTY_ROW;
+  }
   HGE_CUDA(cudaSetDevice(ctx->device));
   hge_algdist* st = new (std::nothrow) hge_algdist();
   if (!st) return HGE_ERR_NOMEM;

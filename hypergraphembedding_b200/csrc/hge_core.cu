@@ -47,7 +47,7 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->own_stream = false;
   ctx->light_max_deg = 64;
-  ctx->chunk = 256;
+  ctx->chunk = 512;
   ctx->blocks_per_sm = 0;  // 0: ask the occupancy calculator
   ctx->launches = 0;
   // NULL selects the legacy default stream, which is also torch's default stream, so work

@@ -46,6 +46,7 @@ struct HgeHalfSchedule {
   int32_t n_partials = 0;
   int32_t chunk_sz = 0;
   int32_t max_deg = 0;
+  int32_t first_empty = -1;       // first row without incidences, or -1
 };
 
 struct hge_incidence {

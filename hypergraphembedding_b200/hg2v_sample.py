@@ -1,0 +1,483 @@
+"""Drop-in for the sampling half of the reference's ``hypergraph_embedding/hg2v_sample.py``:
+``SimilarityRecord``:29, ``_sample_adj_matrix``:53, ``_sample_neighbors``:49, ``BooleanSamples``:125
+(FOBE), ``AlgebraicDistanceSamples``:632 (HOBE) with ``SameTypeDistanceSample``:546 /
+``DiffTypeDistanceSample``:588, and ``SamplesToModelInput``:751.
+
+Same names, arguments, RNG consumption (the process-global legacy numpy stream is advanced
+exactly as the reference advances it) and record contents.  Where the work happens:
+  * candidate rows (scipy CSR-product order) and every draw: csrc/hge_sampler.cpp (host; the
+    MT19937 stream is sequential with data-dependent rejection);
+  * incidence weights and the max-min probabilities of all sampled pairs: csrc/hge_weighting.cu.
+
+The samplers return a ``SampleColumns``: a sequence of ``SimilarityRecord`` backed by columnar
+arrays (a 755k-record result on the youtube fixture is 7 arrays, not 755k tuples); iterating or
+indexing it yields ordinary records, ``list(result)`` materialises them.
+"""
+import collections.abc
+import logging
+from collections import namedtuple
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _native
+from .hypergraph_util import ToCsrMatrix, ToEdgeCsrMatrix
+
+log = logging.getLogger()
+
+SimilarityRecord = namedtuple(
+    "SimilarityRecord",
+    (
+        "left_node_idx",
+        "left_edge_idx",
+        "right_node_idx",
+        "right_edge_idx",
+        "left_weight",  # Only used in weighted cases
+        "right_weight",  # Only used in weighted cases
+        "neighbor_node_indices",
+        "neighbor_node_weights",  # Only used in weighted cases
+        "neighbor_edge_indices",
+        "neighbor_edge_weights",  # Only used in weighted cases
+        "node_node_prob",
+        "edge_edge_prob",
+        "node_edge_prob"))
+# Set all field defaults to none
+SimilarityRecord.__new__.__defaults__ = (None,) * len(SimilarityRecord._fields)
+
+NONE_IDX = -1
+
+
+class SampleColumns(collections.abc.Sequence):
+  """Columnar list of SimilarityRecord.  -1 marks a ``None`` index, NaN a ``None``
+  probability, ``has_neighbors`` False a record without neighbour arrays."""
+
+  FIELDS = ("left_node", "left_edge", "right_node", "right_edge", "neigh_node", "neigh_edge",
+            "nn_prob", "ee_prob", "ne_prob", "has_neighbors")
+
+  def __init__(self, num_neighbors, **cols):
+    self.num_neighbors = int(num_neighbors)
+    for name in self.FIELDS:
+      setattr(self, name, cols[name])
+
+  @classmethod
+  def build(cls, num_neighbors, count, left_node=None, left_edge=None, right_node=None,
+            right_edge=None, neigh_node=None, neigh_edge=None, nn_prob=None, ee_prob=None,
+            ne_prob=None):
+    def idx(a):
+      return np.full(count, NONE_IDX, np.int32) if a is None else np.asarray(a, dtype=np.int32)
+
+    def prob(a):
+      return np.full(count, np.nan, np.float32) if a is None else np.asarray(a, dtype=np.float32)
+
+    k = int(num_neighbors)
+    has = neigh_node is not None
+    none = np.full((count, k), NONE_IDX, np.int32)
+    return cls(k, left_node=idx(left_node), left_edge=idx(left_edge), right_node=idx(right_node),
+               right_edge=idx(right_edge),
+               neigh_node=np.asarray(neigh_node, np.int32).reshape(count, k) if has else none,
+               neigh_edge=np.asarray(neigh_edge, np.int32).reshape(count, k) if has else none.copy(),
+               nn_prob=prob(nn_prob), ee_prob=prob(ee_prob), ne_prob=prob(ne_prob),
+               has_neighbors=np.full(count, has, dtype=bool))
+
+  @classmethod
+  def concatenate(cls, parts):
+    parts = list(parts)
+    k = parts[0].num_neighbors
+    return cls(k, **{name: np.concatenate([getattr(p, name) for p in parts])
+                     for name in cls.FIELDS})
+
+  def arrays(self):
+    return {name: getattr(self, name) for name in self.FIELDS}
+
+  def __len__(self):
+    return len(self.left_node)
+
+  def _record(self, i):
+    def idx(v):
+      return None if v == NONE_IDX else v
+
+    def prob(v):
+      return None if np.isnan(v) else v
+
+    has = bool(self.has_neighbors[i])
+    return SimilarityRecord(
+        left_node_idx=idx(self.left_node[i]), left_edge_idx=idx(self.left_edge[i]),
+        right_node_idx=idx(self.right_node[i]), right_edge_idx=idx(self.right_edge[i]),
+        neighbor_node_indices=self.neigh_node[i] if has else None,
+        neighbor_edge_indices=self.neigh_edge[i] if has else None,
+        node_node_prob=prob(self.nn_prob[i]), edge_edge_prob=prob(self.ee_prob[i]),
+        node_edge_prob=prob(self.ne_prob[i]))
+
+  def __getitem__(self, i):
+    if isinstance(i, slice):
+      return [self._record(j) for j in range(*i.indices(len(self)))]
+    if i < 0:
+      i += len(self)
+    if not 0 <= i < len(self):
+      raise IndexError(i)
+    return self._record(i)
+
+  def __iter__(self):
+    for i in range(len(self)):
+      yield self._record(i)
+
+
+# -----------------------------------------------------------------------------------------
+# sampling primitives
+# -----------------------------------------------------------------------------------------
+
+
+def _sample_neighbors(idx, idx2neighbors, num_neighbors):
+  """hg2v_sample.py:49-51: np.random.choice(neighbours of idx, k, replace=True)."""
+  m = _native.CsrArrays(idx2neighbors)
+  state = _native.LegacyRngState()
+  out = np.empty(num_neighbors, dtype=np.uint32)
+  deg = int(m.ptr[idx + 1] - m.ptr[idx])
+  if deg == 0 and num_neighbors > 0:
+    raise ValueError("'a' cannot be empty unless no samples are taken")
+  if num_neighbors:
+    _native.check(_native.load_library().hge_mt19937_interval(
+        _native.ptr(state.buf), max(deg - 1, 0), num_neighbors, _native.ptr(out)))
+  state.commit()
+  return m.idx[m.ptr[idx] + out.astype(np.int64)]
+
+
+def _sample_adj_matrix(matrix, interesting_rows, samples_per_row, disable_pbar=False,
+                       replace=False, negative=False):
+  """hg2v_sample.py:53-86 on an explicit scipy matrix: list of (row, col) samples.  The row's
+  candidates are its stored columns in stored order (which is what ``matrix[row].nonzero()``
+  returns, sorted or not)."""
+  del disable_pbar
+  rows = list(interesting_rows)
+  if type(samples_per_row) == int:
+    samples_per_row = [samples_per_row for _ in rows]
+  assert len(samples_per_row) == len(rows)
+  assert len(samples_per_row) > 0
+  state = _native.LegacyRngState()
+  r, c = _native.sample_adj_rows((_native.CsrArrays(matrix),), rows, samples_per_row, state,
+                                 replace=replace, negative=negative)
+  state.commit()
+  return list(zip(r.tolist(), c.tolist()))
+
+
+def _alpha_scale(val, alpha=0):
+  """hg2v_sample.py:89-94."""
+  assert alpha >= 0
+  assert alpha <= 1
+  assert val <= 1
+  assert val >= 0
+  return alpha + (1 - alpha) * (val)
+
+
+class _Graph(object):
+  """Host CSR arrays of a hypergraph proto the way the samplers see it: A from ``node.edges``
+  (ToCsrMatrix), B from ``edge.nodes`` (ToEdgeCsrMatrix), their transposes for the products
+  ``A * A.T`` / ``B * B.T``, and the proto-map iteration orders."""
+
+  def __init__(self, hypergraph):
+    A = ToCsrMatrix(hypergraph)
+    B = ToEdgeCsrMatrix(hypergraph)
+    n = max(A.shape[0], B.shape[1])
+    e = max(A.shape[1], B.shape[0])
+    A = sps.csr_matrix((A.data, A.indices, _pad(A.indptr, n)), shape=(n, e))
+    B = sps.csr_matrix((B.data, B.indices, _pad(B.indptr, e)), shape=(e, n))
+    At = A.T.tocsr()
+    At.sort_indices()
+    consistent = (At.nnz == B.nnz and np.array_equal(At.indptr, B.indptr) and
+                  np.array_equal(At.indices, B.indices))
+    self.A, self.B = A, B
+    self.a, self.b = _native.CsrArrays(A), _native.CsrArrays(B)
+    if consistent:
+      self.at, self.bt = self.b, self.a
+    else:
+      Bt = B.T.tocsr()
+      Bt.sort_indices()
+      self.at, self.bt = _native.CsrArrays(At), _native.CsrArrays(Bt)
+    self.node_rows = list(hypergraph.node)
+    self.edge_rows = list(hypergraph.edge)
+    self.num_nodes, self.num_edges = n, e
+
+  def incidence(self, ctx):
+    return _native.Incidence(ctx, self.num_nodes, self.num_edges, self.a.ptr, self.a.idx,
+                             self.b.ptr, self.b.idx)
+
+
+def _pad(indptr, rows):
+  indptr = np.asarray(indptr)
+  if len(indptr) - 1 >= rows:
+    return indptr
+  return np.concatenate([indptr, np.full(rows - (len(indptr) - 1), indptr[-1], indptr.dtype)])
+
+
+def embedding_to_arrays(embedding, num_nodes, num_edges):
+  """Dense fp32 [num_nodes, R] / [num_edges, R] from a HypergraphEmbedding proto."""
+  dim = None
+  for vec in embedding.node.values():
+    dim = len(vec.values)
+    break
+  assert dim is not None and dim > 0, "embedding has no node vectors"
+  xn = np.zeros((num_nodes, dim), dtype=np.float32)
+  xe = np.zeros((num_edges, dim), dtype=np.float32)
+  for idx, vec in embedding.node.items():
+    if 0 <= idx < num_nodes:
+      xn[idx] = vec.values
+  for idx, vec in embedding.edge.items():
+    if 0 <= idx < num_edges:
+      xe[idx] = vec.values
+  return xn, xe
+
+
+################################################################################
+# BooleanSamples                                                               #
+################################################################################
+
+
+def BooleanSamples(hypergraph, num_neighbors, num_samples, neg_samples=0, disable_pbar=False):
+  """hg2v_sample.py:125-242 (FOBE): up to num_samples node-node, edge-edge and node-edge /
+  edge-node first-order samples per row with probability 1, optionally neg_samples uniform
+  negatives per row (including the reference's duplicated edge-edge negative block, :215-221)."""
+  del disable_pbar
+  node_samples = [int(node.weight * num_samples) for _, node in hypergraph.node.items()]
+  edge_samples = [int(edge.weight * num_samples) for _, edge in hypergraph.edge.items()]
+  neg_node_samples = [int(node.weight * neg_samples) for _, node in hypergraph.node.items()]
+  neg_edge_samples = [int(edge.weight * neg_samples) for _, edge in hypergraph.edge.items()]
+
+  g = _Graph(hypergraph)
+  k = num_neighbors
+  state = _native.LegacyRngState()
+  parts = []
+
+  log.info("Sampling node-node probabilities")
+  r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, node_samples, state)
+  parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c,
+                                   nn_prob=np.ones(len(r), np.float32)))
+  log.info("Sampling edge-edge probabilities")
+  r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, edge_samples, state)
+  parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c,
+                                   ee_prob=np.ones(len(r), np.float32)))
+  log.info("Getting node-edge relationships")
+  n1, e1 = _native.sample_adj_rows((g.a,), g.node_rows, node_samples, state)
+  log.info("Getting edge-node relationships")
+  e2, n2 = _native.sample_adj_rows((g.b,), g.edge_rows, edge_samples, state)
+  nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
+  nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state)
+  parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
+                                   neigh_node=nbr_n, neigh_edge=nbr_e,
+                                   ne_prob=np.ones(len(nodes), np.float32)))
+
+  if neg_samples > 0:
+    log.info("Node-Node Negatives")
+    r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, neg_node_samples, state, negative=True)
+    parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c))
+    for label in ("Edge-Edge Negatives", "Node-Edge Negatives"):   # sic: both are edge-edge
+      log.info(label)
+      r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, neg_edge_samples, state,
+                                     negative=True)
+      parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c))
+    log.info("Getting node-edge negatives")
+    n1, e1 = _native.sample_adj_rows((g.a,), g.node_rows, neg_node_samples, state, negative=True)
+    log.info("Getting edge-node negatives")
+    e2, n2 = _native.sample_adj_rows((g.b,), g.edge_rows, neg_edge_samples, state, negative=True)
+    nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
+    nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state)
+    parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
+                                     neigh_node=nbr_n, neigh_edge=nbr_e))
+  state.commit()
+  return SampleColumns.concatenate(parts)
+
+
+################################################################################
+# AlgebraicDistanceSamples - With helpers                                      #
+################################################################################
+
+
+class _HobeWeights(object):
+  """Incidence weights W(n, e) = (sqrt(R) - ||xn[n] - xe[e]||) / sqrt(R) in both storage
+  orders, resident on the device; every w(.,.) the reference evaluates is one of them
+  (SURVEY.md section 0.2)."""
+
+  def __init__(self, graph, xn, xe, ctx=None):
+    import torch
+    self.ctx = ctx or _native.default_context()
+    self.graph = graph
+    self.inc = graph.incidence(self.ctx)
+    dev = torch.device("cuda", self.ctx.device)
+    xn_d = torch.from_numpy(np.ascontiguousarray(xn, dtype=np.float32)).to(dev)
+    xe_d = torch.from_numpy(np.ascontiguousarray(xe, dtype=np.float32)).to(dev)
+    self.w_n2e = _native.incidence_l2(self.ctx, self.inc, xn_d, xe_d, order=0, as_weight=True)
+    self.w_e2n = _native.incidence_l2(self.ctx, self.inc, xn_d, xe_d, order=1, as_weight=True)
+    self.dev = dev
+
+  def _dev(self, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev)
+
+  def same_type(self, side, pi, pj):
+    w = self.w_n2e if side == 0 else self.w_e2n
+    return _native.same_type_prob(self.ctx, self.inc, side, w, self._dev(pi),
+                                  self._dev(pj)).cpu().numpy()
+
+  def diff_type(self, pn, pe):
+    return _native.diff_type_prob(self.ctx, self.inc, self.w_e2n, self._dev(pn),
+                                  self._dev(pe)).cpu().numpy()
+
+  def close(self):
+    self.inc.close()
+
+
+def _same_type_dist_calc(indices, idx2target, source_half_emb, target_half_emb):
+  """hg2v_sample.py:527-543 for one pair (compat entry point; the samplers batch this)."""
+  m = sps.csr_matrix(idx2target)
+  n_src, n_tgt = m.shape
+  xs = np.zeros((n_src, len(source_half_emb[indices[0]].values)), np.float32)
+  xt = np.zeros((n_tgt, xs.shape[1]), np.float32)
+  for i in (indices[0], indices[1]):
+    xs[i] = source_half_emb[i].values
+  for k in set(m[indices[0]].indices) | set(m[indices[1]].indices):
+    xt[k] = target_half_emb[int(k)].values
+  ctx = _native.default_context()
+  ptr_, idx_ = _native.CsrArrays(m).ptr, _native.CsrArrays(m).idx
+  mt = m.T.tocsr()
+  mt.sort_indices()
+  inc = _native.Incidence(ctx, n_src, n_tgt, ptr_, idx_, np.asarray(mt.indptr, np.int64),
+                          np.asarray(mt.indices, np.int32))
+  try:
+    w = _native.incidence_l2(ctx, inc, xs, xt, order=0, as_weight=True)
+    prob = _native.same_type_prob(ctx, inc, 0, w, [indices[0]], [indices[1]])[0]
+  finally:
+    inc.close()
+  has_shared = len(set(m[indices[0]].indices) & set(m[indices[1]].indices)) > 0
+  return prob if has_shared else 0
+
+
+def AlgebraicDistanceSamples(hypergraph, algebraic_embedding, num_neighbors, num_samples,
+                             run_in_parallel=True, disable_pbar=False):
+  """hg2v_sample.py:632-717 (HOBE): node-node, edge-edge and node-edge samples whose
+  probability is the max-min algebraic-distance weight over shared neighbours.
+
+  Pair sets are drawn from the global RNG exactly as the reference's parent process draws
+  them.  The neighbour arrays of node-edge records are drawn by the reference inside forked
+  workers that inherit a copy of the parent's RNG; this implementation reproduces the
+  ``run_in_parallel=False`` behaviour (one worker, records in order) for either flag value,
+  and like the reference leaves the global RNG where the pair sampling left it."""
+  del run_in_parallel, disable_pbar
+  log.info("Performing input checks")
+  assert num_neighbors >= 0
+  assert num_samples >= 0
+
+  g = _Graph(hypergraph)
+  k = num_neighbors
+  xn, xe = embedding_to_arrays(algebraic_embedding, g.num_nodes, g.num_edges)
+  weights = _HobeWeights(g, xn, xe)
+  try:
+    state = _native.LegacyRngState()
+    parts = []
+    log.info("Getting node-node samples")
+    per_node = [num_samples] * len(g.node_rows)
+    per_edge = [num_samples] * len(g.edge_rows)
+    r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, per_node, state)
+    log.info("Sampling node-node probabilities")
+    parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c,
+                                     nn_prob=weights.same_type(0, r, c)))
+    log.info("Getting edge-edge samples")
+    r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, per_edge, state)
+    log.info("Sampling edge-edge probabilities")
+    parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c,
+                                     ee_prob=weights.same_type(1, r, c)))
+    log.info("Getting node-edge samples")
+    n1, e1 = _native.sample_adj_rows((g.a, g.at, g.a), g.node_rows, per_node, state)
+    log.info("Getting edge-node samples")
+    e2, n2 = _native.sample_adj_rows((g.b, g.bt, g.b), g.edge_rows, per_edge, state)
+    state.commit()   # the parent's stream ends here (workers draw from a copy)
+    nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
+    nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state.copy())
+    parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
+                                     neigh_node=nbr_n, neigh_edge=nbr_e,
+                                     ne_prob=weights.diff_type(nodes, edges)))
+  finally:
+    weights.close()
+  return SampleColumns.concatenate(parts)
+
+
+def SameTypeDistanceSample(indices, idx2target=None, source_half_emb=None, target_half_emb=None,
+                           is_edge=None):
+  """hg2v_sample.py:546-576 with explicit arguments (the reference's worker-global fallback
+  does not exist here: there are no worker processes)."""
+  assert idx2target is not None and source_half_emb is not None and target_half_emb is not None
+  prob = _same_type_dist_calc(indices, idx2target, source_half_emb, target_half_emb)
+  if is_edge:
+    return SimilarityRecord(left_edge_idx=indices[0], right_edge_idx=indices[1],
+                            edge_edge_prob=_alpha_scale(prob))
+  return SimilarityRecord(left_node_idx=indices[0], right_node_idx=indices[1],
+                          node_node_prob=_alpha_scale(prob))
+
+
+################################################################################
+# Samples to Model Input w/ Helper functions                                   #
+################################################################################
+
+
+def _columns_to_model_input(cols, num_neighbors, weighted):
+  m = len(cols)
+  zeros_i = np.zeros(m, dtype=np.int32)
+  zeros_f = np.zeros(m, dtype=np.float32)
+
+  def inc(a):
+    return (a + 1).astype(np.int32)      # -1 (None) becomes the padding index 0
+
+  def neigh(a):
+    out = []
+    for i in range(num_neighbors):
+      out.append(inc(a[:, i]) if i < a.shape[1] else zeros_i.copy())
+    return out
+
+  features = [inc(cols.left_node), inc(cols.left_edge), inc(cols.right_node), inc(cols.right_edge)]
+  if weighted:
+    features += [zeros_f.copy(), zeros_f.copy()]
+  features += neigh(cols.neigh_node)
+  if weighted:
+    features += [zeros_f.copy() for _ in range(num_neighbors)]
+  features += neigh(cols.neigh_edge)
+  if weighted:
+    features += [zeros_f.copy() for _ in range(num_neighbors)]
+  targets = [np.nan_to_num(cols.nn_prob, nan=0.0), np.nan_to_num(cols.ee_prob, nan=0.0),
+             np.nan_to_num(cols.ne_prob, nan=0.0)]
+  return (features, targets)
+
+
+def SamplesToModelInput(similarity_records, num_neighbors, weighted=True):
+  """hg2v_sample.py:751-797: (input arrays, output arrays).  Indices are shifted by +1 because
+  0 is the padding row of the embedding tables; None becomes 0; neighbour lists are padded
+  to num_neighbors.  A ``SampleColumns`` is packed column-wise into numpy arrays; any other
+  iterable of records goes through the reference's record loop and yields Python lists."""
+  if isinstance(similarity_records, SampleColumns):
+    return _columns_to_model_input(similarity_records, num_neighbors, weighted)
+
+  records = list(similarity_records)
+
+  def scalar(field, shift):
+    # None -> 0; indices are shifted past the padding row
+    return [0 if getattr(r, field) is None else getattr(r, field) + shift for r in records]
+
+  def padded(field, shift):
+    cols = []
+    for i in range(num_neighbors):
+      col = []
+      for r in records:
+        arr = getattr(r, field)
+        col.append(0 if arr is None or i >= len(arr) else arr[i] + shift)
+      cols.append(col)
+    return cols
+
+  features = [scalar("left_node_idx", 1), scalar("left_edge_idx", 1), scalar("right_node_idx", 1),
+              scalar("right_edge_idx", 1)]
+  if weighted:
+    features += [scalar("left_weight", 0), scalar("right_weight", 0)]
+  features += padded("neighbor_node_indices", 1)
+  if weighted:
+    features += padded("neighbor_node_weights", 0)
+  features += padded("neighbor_edge_indices", 1)
+  if weighted:
+    features += padded("neighbor_edge_weights", 0)
+  targets = [scalar("node_node_prob", 0), scalar("edge_edge_prob", 0), scalar("node_edge_prob", 0)]
+  return (features, targets)

@@ -71,7 +71,8 @@ int64_t hge_ctx_launch_count(const hge_ctx* ctx);
  * CSC of the same matrix when the hypergraph is consistent).  Column ids must be sorted
  * and unique inside a row, as scipy's canonical CSR is.  Builds the degree-binned gather
  * schedule and the inverse neighbour-weight sums used by the relaxation.
- * Returns HGE_ERR_EMPTY_ROW if any of the N nodes / E edges has no incidence. */
+ * Rows without incidences are accepted here (the weighting entry points work on sparse id
+ * ranges); the relaxation refuses them with HGE_ERR_EMPTY_ROW (hge_algdist_create / _run). */
 int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                          const int64_t* n2e_ptr, const int32_t* n2e_idx,
                          const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
@@ -109,6 +110,96 @@ int hge_algdist_edge_finalize(hge_algdist* st, int sweep, const float* partial,
 int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out);
 int hge_algdist_ld(const hge_algdist* st);
 int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, int mem);
+
+/* ---- distances and HOBE / FOBE weights ------------------------------------------------
+ * All vectors are dense fp32 [rows, R]; outputs are fp32.  `mem` applies to every array
+ * argument of a call. */
+
+/* dist[p] = || xn[n] - xe[e] ||_2 for every stored incidence p, in the storage order of the
+ * node->edge CSR (order == 0) or of the edge->node CSR (order == 1).  Replaces the per-pair
+ * np.linalg.norm of WeightByDistance (hg2v_weighting.py:86-91) and of _same_type_dist_calc
+ * (hg2v_sample.py:540-541).  With as_weight != 0 the HOBE incidence weight
+ * (sqrt(R) - d) / sqrt(R) is stored instead (hg2v_sample.py:537-541). */
+int hge_incidence_l2(hge_ctx* ctx, hge_incidence* inc, const float* xn, const float* xe, int R,
+                     int order, int as_weight, float* dist, int mem);
+
+/* dist[p] = || xa[ia[p]] - xb[ib[p]] ||_2 for arbitrary (node,node), (node,edge) or
+ * (edge,edge) sample pairs: the distance part of WeightBySameTypeDistance
+ * (hg2v_weighting.py:37-45) and of the 100M-pair weighting of BASELINE.json configs[2]. */
+int hge_pair_l2(hge_ctx* ctx, const float* xa, int64_t rows_a, const float* xb, int64_t rows_b,
+                int R, const int32_t* ia, const int32_t* ib, int64_t num_pairs, float* dist,
+                int mem);
+
+/* In place: v <- alpha + (1 - alpha) * (1 - (v - min) / (max - min)), min / max over all n
+ * values; a zero range maps every value to alpha + (1 - alpha) * 0.  This is
+ * AlphaScaleValues(OneMinusValues(ZeroOneScaleValues(.))) (hg2v_weighting.py:301-333) with the
+ * reference's fp32 operation order, so equal inputs give bit-equal outputs.  minmax (optional,
+ * host, 2 floats) receives (min, max).  alpha outside [0, 1] is HGE_ERR_INVALID. */
+int hge_scale_transform(hge_ctx* ctx, float* values, int64_t n, double alpha, float* minmax,
+                        int mem);
+
+/* span[r] = max(0, max over neighbours b and components c of (x_other[b][c] - x_self[r][c]))
+ *         - min(0, min over the same set), for the rows of the node->edge CSR (side == 0,
+ * x_self = xn) or of the edge->node CSR (side == 1, x_self = xe): _compute_span
+ * (hg2v_weighting.py:214-233). */
+int hge_row_span(hge_ctx* ctx, hge_incidence* inc, const float* xn, const float* xe, int R,
+                 int side, float* span, int mem);
+
+/* HOBE same-type probability (hg2v_sample.py:527-543) for num_pairs pairs (i, j) of rows of
+ * the node->edge CSR (side == 0) or of the edge->node CSR (side == 1):
+ *     prob = max over shared columns k of min(w(i,k), w(j,k)),  0 without a shared column,
+ * with w the incidence weights in that CSR's storage order (hge_incidence_l2, as_weight). */
+int hge_same_type_prob(hge_ctx* ctx, hge_incidence* inc, int side, const float* w,
+                       const int32_t* pi, const int32_t* pj, int64_t num_pairs, float* prob,
+                       int mem);
+
+/* HOBE node-edge probability (hg2v_sample.py:606-629) for pairs (node n, edge e):
+ *     prob = max(0, max over the node's edges e' of same_type_prob_edges(e, e')),
+ * w_e2n = incidence weights in edge->node storage order. */
+int hge_diff_type_prob(hge_ctx* ctx, hge_incidence* inc, const float* w_e2n, const int32_t* pn,
+                       const int32_t* pe, int64_t num_pairs, float* prob, int mem);
+
+/* ---- candidate rows and bit-exact sampling (host code; all pointers are host pointers) ---
+ * The reference draws every sample from numpy's process-global legacy MT19937, sequentially
+ * and with data-dependent rejection, so this part of the path runs on the host; the drawn
+ * pairs are then weighted on the GPU.  state625 = the 624 key words of
+ * np.random.get_state() followed by its `pos`; it is advanced in place. */
+
+/* Next n raw 32-bit outputs / n bounded integers in [0, max_inclusive] (numpy rk_interval:
+ * masked rejection; max 0 consumes nothing).  Test hooks for the stream replay. */
+int hge_mt19937_random_raw(uint32_t* state625, int64_t n, uint32_t* out);
+int hge_mt19937_interval(uint32_t* state625, uint32_t max_inclusive, int64_t n, uint32_t* out);
+
+/* Rows of M1 (kind 0), M1*M2 (kind 1) or (M1*M2)*M3 (kind 2) as boolean CSR, for the listed
+ * rows, in the column order scipy's csr_matmat stores them (reverse first-discovery order;
+ * this is the candidate order of _sample_adj_matrix, hg2v_sample.py:77) or sorted
+ * (sorted != 0: the nonzero pattern used by WeightBySameTypeDistance, hg2v_weighting.py:56-61).
+ * mid_cols / out_cols = column counts of M1*M2 and of the final product.  With out_idx == NULL
+ * only out_ptr (num_rows + 1 entries) is filled, so the caller can size out_idx. */
+int hge_spgemm_rows(int kind, const int64_t* p1, const int32_t* i1, const int64_t* p2,
+                    const int32_t* i2, const int64_t* p3, const int32_t* i3, int32_t mid_cols,
+                    int32_t out_cols, const int32_t* rows, int64_t num_rows, int sorted,
+                    int64_t* out_ptr, int32_t* out_idx, int64_t capacity);
+
+/* _sample_adj_matrix (hg2v_sample.py:53-86) over the same three kinds of matrix: for each
+ * listed row, in order, either `samples_per_row` uniform columns in [0, out_cols) (negative),
+ * or a draw without / with replacement from the row's candidates (np.random.choice; at most
+ * len(candidates) without replacement; rows without candidates are skipped).  Emits (row, col)
+ * pairs; capacity must be >= sum(samples_per_row). */
+int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const int64_t* p2,
+                        const int32_t* i2, const int64_t* p3, const int32_t* i3, int32_t mid_cols,
+                        int32_t out_cols, const int32_t* rows, int64_t num_rows,
+                        const int32_t* samples_per_row, int replace, int negative,
+                        uint32_t* state625, int32_t* out_row, int32_t* out_col, int64_t capacity,
+                        int64_t* out_count);
+
+/* _sample_neighbors (hg2v_sample.py:49-51) for a list of (node, edge) samples: per sample k
+ * draws with replacement from the node's edges, then k from the edge's nodes
+ * (hg2v_sample.py:184-187, 604-605).  Outputs are [num_samples, k]. */
+int hge_sample_neighbors(const int64_t* n2e_ptr, const int32_t* n2e_idx, const int64_t* e2n_ptr,
+                         const int32_t* e2n_idx, const int32_t* nodes, const int32_t* edges,
+                         int64_t num_samples, int k, uint32_t* state625, int32_t* out_nbr_edges,
+                         int32_t* out_nbr_nodes);
 
 #ifdef __cplusplus
 }

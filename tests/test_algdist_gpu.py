@@ -135,7 +135,7 @@ def test_tuning_knobs_do_not_change_results(gpu_ctx):
       xn, xe = _run(A, xn0, xe0, 5, gpu_ctx)
       assert np.abs(xn - base[0]).max() < 2e-6 and np.abs(xe - base[1]).max() < 2e-6
   finally:
-    gpu_ctx.set_tuning(64, 256, 0)
+    gpu_ctx.set_tuning(64, 512, 0)
 
 
 def test_results_are_reproducible_run_to_run(gpu_ctx):
