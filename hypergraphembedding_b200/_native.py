@@ -64,8 +64,12 @@ SIGNATURES = {
     "hge_algdist_load": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
     "hge_algdist_node_half": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "hge_algdist_edge_half": (ctypes.c_int, [c_vp, ctypes.c_int]),
-    "hge_algdist_edge_partial": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
-    "hge_algdist_edge_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
+    "hge_algdist_edge_partial": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "hge_algdist_edge_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "hge_incidence_create_sharded": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp,
+                                                    c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "hge_incidence_slice_range": (ctypes.c_int, [c_vp, ctypes.c_int, c_i32p, c_i32p]),
     "hge_algdist_minmax_ptr": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "hge_algdist_ld": (ctypes.c_int, [c_vp]),
     "hge_algdist_store": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int]),
@@ -220,9 +224,11 @@ def _as_i32(a):
 
 
 class Incidence(object):
-  """Device-resident incidence (hge_incidence): int32 CSR of node->edge and edge->node."""
+  """Device-resident incidence (hge_incidence): int32 CSR of node->edge and edge->node.  With
+  `edge_deg_global` / `edge_inv_s_global` it is one shard of a node-partitioned hypergraph."""
 
-  def __init__(self, ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx):
+  def __init__(self, ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
+               edge_deg_global=None, edge_inv_s_global=None, num_slices=1):
     self.ctx = ctx
     self.num_nodes = int(num_nodes)
     self.num_edges = int(num_edges)
@@ -236,10 +242,20 @@ class Incidence(object):
       keep = (_as_i64(n2e_ptr), _as_i32(n2e_idx), _as_i64(e2n_ptr), _as_i32(e2n_idx))
     self._keep = keep
     handle = c_vp()
-    check(ctx.lib.hge_incidence_create(ctx.handle, self.num_nodes, self.num_edges, ptr(keep[0]),
-                                       ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
-                                       MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)),
-          "hge_incidence_create")
+    self.num_slices = int(num_slices)
+    if edge_deg_global is None:
+      check(ctx.lib.hge_incidence_create(ctx.handle, self.num_nodes, self.num_edges, ptr(keep[0]),
+                                         ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
+                                         MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)),
+            "hge_incidence_create")
+    else:
+      if not device:
+        edge_deg_global = _as_i32(edge_deg_global)
+        edge_inv_s_global = np.ascontiguousarray(edge_inv_s_global, dtype=np.float32)
+      check(ctx.lib.hge_incidence_create_sharded(
+          ctx.handle, self.num_nodes, self.num_edges, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]),
+          ptr(keep[3]), ptr(edge_deg_global), ptr(edge_inv_s_global), self.num_slices,
+          MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)), "hge_incidence_create_sharded")
     self.handle = handle
     self.nnz_n2e = int(keep[1].shape[0])
     self.nnz_e2n = int(keep[3].shape[0])
@@ -252,6 +268,12 @@ class Incidence(object):
 
   def nnz_of(self, order):
     return self.nnz_n2e if order == 0 else self.nnz_e2n
+
+  def slice_range(self, slice_index):
+    r0, r1 = ctypes.c_int32(), ctypes.c_int32()
+    check(self.ctx.lib.hge_incidence_slice_range(self.handle, slice_index, ctypes.byref(r0),
+                                                 ctypes.byref(r1)), "hge_incidence_slice_range")
+    return r0.value, r1.value
 
   def close(self):
     if getattr(self, "handle", None):
@@ -301,11 +323,13 @@ class AlgDistState(object):
   def edge_half(self, sweep):
     check(self.ctx.lib.hge_algdist_edge_half(self.handle, sweep), "hge_algdist_edge_half")
 
-  def edge_partial(self, sweep, partial):
-    check(self.ctx.lib.hge_algdist_edge_partial(self.handle, sweep, ptr(partial)))
+  def edge_partial(self, sweep, slice_index, partial):
+    check(self.ctx.lib.hge_algdist_edge_partial(self.handle, sweep, slice_index, ptr(partial)),
+          "hge_algdist_edge_partial")
 
-  def edge_finalize(self, sweep, partial, inv_s_edge=None):
-    check(self.ctx.lib.hge_algdist_edge_finalize(self.handle, sweep, ptr(partial), ptr(inv_s_edge)))
+  def edge_finalize(self, sweep, slice_index, partial):
+    check(self.ctx.lib.hge_algdist_edge_finalize(self.handle, sweep, slice_index, ptr(partial)),
+          "hge_algdist_edge_finalize")
 
   def minmax_ptr(self, sweep):
     out = c_vp()

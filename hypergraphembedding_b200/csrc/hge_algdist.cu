@@ -386,14 +386,10 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
           nxt[k] = (k * LPR + gl < 8 && t < deg) ? __ldcs(ridx + t) : -1;
         }
         float4 v[8];
-        const int live = maxdeg - base;   // warp-uniform: rows are sorted by degree, so the
-#pragma unroll                            // slots past the longest row of the quad are skipped
+#pragma unroll
         for (int t = 0; t < 8; ++t) {
-          v[t] = hge_f4_zero();
-          if (t < live) {
-            const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
-            if (c >= 0 && active) v[t] = __ldg(a.yg + (size_t)c * ld4 + c4);
-          }
+          const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
+          v[t] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
         }
         accumulate<8>(acc, comp, v);
 #pragma unroll
@@ -447,7 +443,8 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
 }
 
 // Sharded edge half, second part: the raw sums have been all-reduced over the shards.
-__global__ void k_edge_finalize(int64_t rows, int R, int ld, const float* __restrict__ raw,
+__global__ void k_edge_finalize(int64_t row0, int64_t rows, int R, int ld,
+                                const float* __restrict__ raw,
                                 const int32_t* __restrict__ deg, const float* __restrict__ invs,
                                 const int32_t* __restrict__ mm_prev, int32_t* __restrict__ mm_cur,
                                 float* __restrict__ y) {
@@ -459,8 +456,9 @@ __global__ void k_edge_finalize(int64_t rows, int R, int ld, const float* __rest
   }
   __syncthreads();
   const int64_t total = rows * ld;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = row0 * ld + j;
     const int64_t r = i / ld;
     const int c = (int)(i - r * ld);
     if (c >= R) continue;
@@ -496,34 +494,36 @@ int grid_1d(const hge_ctx* ctx, int64_t work, int block) {
   return (int)std::min(want, cap);
 }
 
-int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& h_ptr,
-                        const int64_t* d_ptr, const int32_t* d_idx, const int32_t* d_own_deg,
-                        const int32_t* d_other_deg, bool allow_empty, const char* what,
-                        HgeHalfSchedule* s) {
-  s->rows = rows;
-  s->nnz = h_ptr[rows];
-  s->ptr = d_ptr;
-  s->idx = d_idx;
+// invs[r] = 1 / sum over the row's neighbours b of 1 / other_deg[b], computed on the device.
+int compute_invs(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, const int32_t* d_idx,
+                 const int32_t* d_other_deg, float** invs, std::vector<float>* h_invs) {
+  HGE_TRY(hge_dev_alloc(ctx, invs, (size_t)rows));
+  k_row_invs<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
+      rows, d_ptr, d_idx, d_other_deg, *invs);
+  HGE_CHECK_LAUNCH(ctx);
+  h_invs->resize((size_t)rows);
+  HGE_CUDA(cudaMemcpyAsync(h_invs->data(), *invs, (size_t)rows * sizeof(float),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HGE_OK;
+}
+
+// Work items for rows [row0, row1) of one CSR.  ptr / idx / deg / invs of `s` are set by the
+// caller (slices of the sharded edge half share them).
+int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
+                        const std::vector<int64_t>& h_ptr, const std::vector<float>& h_invs,
+                        const char* what, HgeHalfSchedule* s) {
+  s->rows = row1 - row0;
+  s->nnz = h_ptr[row1] - h_ptr[row0];
   s->chunk_sz = ctx->chunk;
   const int light_max = ctx->light_max_deg;
   const int chunk = ctx->chunk;
-
-  // inverse neighbour-weight sums, on the device
-  HGE_TRY(hge_dev_alloc(ctx, &s->invs, (size_t)rows));
-  k_row_invs<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
-      rows, d_ptr, d_idx, d_other_deg, s->invs);
-  HGE_CHECK_LAUNCH(ctx);
-  std::vector<float> h_invs((size_t)rows);
-  HGE_CUDA(cudaMemcpyAsync(h_invs.data(), s->invs, (size_t)rows * sizeof(float),
-                           cudaMemcpyDeviceToHost, ctx->stream));
-  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
-  (void)d_own_deg;
 
   // counting sort of the light rows by descending degree; long rows sorted by degree too
   std::vector<int64_t> bucket((size_t)light_max + 2, 0);
   std::vector<std::pair<int32_t, int32_t>> heavy;  // (deg, row)
   int32_t max_deg = 0;
-  for (int32_t r = 0; r < rows; ++r) {
+  for (int32_t r = row0; r < row1; ++r) {
     const int64_t d = h_ptr[r + 1] - h_ptr[r];
     if (d <= 0) {
       if (d < 0) {
@@ -531,7 +531,6 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
         return HGE_ERR_INVALID;
       }
       if (s->first_empty < 0) s->first_empty = r;
-      (void)allow_empty;
     }
     if (d > INT32_MAX) {
       hge_set_error("%s %d has more than 2^31-1 incidences", what, r);
@@ -551,7 +550,7 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
   }
   s->n_light = run;
   std::vector<HgeLightItem> light((size_t)run);
-  for (int32_t r = 0; r < rows; ++r) {
+  for (int32_t r = row0; r < row1; ++r) {
     const int64_t d = h_ptr[r + 1] - h_ptr[r];
     if (d > light_max) continue;
     HgeLightItem it;
@@ -606,9 +605,11 @@ int build_half_schedule(hge_ctx* ctx, int32_t rows, const std::vector<int64_t>& 
   return HGE_OK;
 }
 
-void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s) {
-  hge_dev_free(ctx, s->deg);
-  hge_dev_free(ctx, s->invs);
+void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays = true) {
+  if (owns_arrays) {
+    hge_dev_free(ctx, s->deg);
+    hge_dev_free(ctx, s->invs);
+  }
   hge_dev_free(ctx, s->light);
   hge_dev_free(ctx, s->hrows);
   hge_dev_free(ctx, s->chunks);
@@ -655,9 +656,10 @@ int occupancy_grid(const hge_ctx* ctx, int* out) {
   return HGE_OK;
 }
 
-int run_half(hge_algdist* st, bool node_half, int sweep, float* raw) {
+int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice = -1) {
   hge_incidence* inc = st->inc;
-  const HgeHalfSchedule& s = node_half ? inc->node_half : inc->edge_half;
+  const HgeHalfSchedule& s = node_half ? inc->node_half
+                                       : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
   HalfSweepArgs a;
   a.idx = s.idx;
   a.yg = reinterpret_cast<const float4*>(node_half ? st->ye : st->yn);
@@ -692,16 +694,20 @@ int run_half(hge_algdist* st, bool node_half, int sweep, float* raw) {
 
 extern "C" {
 
-int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
-                         const int64_t* n2e_ptr, const int32_t* n2e_idx,
-                         const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
-                         hge_incidence** out) {
-  HGE_REQUIRE(ctx && out, "hge_incidence_create: NULL ctx / out");
+static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
+                                 const int64_t* n2e_ptr, const int32_t* n2e_idx,
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
+                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
+                                 int num_slices, int mem, hge_incidence** out) {
+  const char* fn = edge_deg_global ? "hge_incidence_create_sharded" : "hge_incidence_create";
+  HGE_REQUIRE(ctx && out, "%s: NULL ctx / out", fn);
   *out = nullptr;
-  HGE_REQUIRE(num_nodes > 0 && num_edges > 0, "hge_incidence_create: empty hypergraph (%d nodes, %d edges)",
+  HGE_REQUIRE(num_nodes > 0 && num_edges > 0, "%s: empty hypergraph (%d nodes, %d edges)", fn,
               num_nodes, num_edges);
-  HGE_REQUIRE(n2e_ptr && n2e_idx && e2n_ptr && e2n_idx, "hge_incidence_create: NULL CSR array");
-  HGE_REQUIRE(mem == HGE_MEM_HOST || mem == HGE_MEM_DEVICE, "hge_incidence_create: bad mem %d", mem);
+  HGE_REQUIRE(n2e_ptr && n2e_idx && e2n_ptr && e2n_idx, "%s: NULL CSR array", fn);
+  HGE_REQUIRE(mem == HGE_MEM_HOST || mem == HGE_MEM_DEVICE, "%s: bad mem %d", fn, mem);
+  HGE_REQUIRE(num_slices >= 1 && num_slices <= 64 && num_slices <= num_edges,
+              "%s: num_slices %d not in [1, min(64, edges)]", fn, num_slices);
   HGE_CUDA(cudaSetDevice(ctx->device));
 
   hge_incidence* inc = new (std::nothrow) hge_incidence();
@@ -709,6 +715,7 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
   inc->ctx = ctx;
   inc->N = num_nodes;
   inc->E = num_edges;
+  inc->sharded = edge_deg_global != nullptr;
   int rc = HGE_OK;
   auto fail = [&](int code) {
     hge_incidence_destroy(inc);
@@ -717,6 +724,7 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
 
   inc->h_n2e_ptr.resize((size_t)num_nodes + 1);
   inc->h_e2n_ptr.resize((size_t)num_edges + 1);
+  cudaError_t e = cudaSuccess;
   if (mem == HGE_MEM_HOST) {
     std::copy(n2e_ptr, n2e_ptr + num_nodes + 1, inc->h_n2e_ptr.begin());
     std::copy(e2n_ptr, e2n_ptr + num_edges + 1, inc->h_e2n_ptr.begin());
@@ -726,7 +734,6 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
     if ((rc = hge_dev_alloc(ctx, &inc->e2n_ptr, (size_t)num_edges + 1)) != HGE_OK) return fail(rc);
     if ((rc = hge_dev_alloc(ctx, &inc->n2e_idx, (size_t)nnz_a)) != HGE_OK) return fail(rc);
     if ((rc = hge_dev_alloc(ctx, &inc->e2n_idx, (size_t)nnz_b)) != HGE_OK) return fail(rc);
-    cudaError_t e = cudaSuccess;
     auto up = [&](void* d, const void* h, size_t bytes) {
       if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
@@ -735,7 +742,7 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
     up(inc->n2e_idx, n2e_idx, (size_t)nnz_a * 4);
     up(inc->e2n_idx, e2n_idx, (size_t)nnz_b * 4);
     if (e != cudaSuccess) {
-      hge_set_error("hge_incidence_create: upload failed: %s", cudaGetErrorString(e));
+      hge_set_error("%s: upload failed: %s", fn, cudaGetErrorString(e));
       return fail(HGE_ERR_CUDA);
     }
   } else {
@@ -744,42 +751,120 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
     inc->e2n_ptr = const_cast<int64_t*>(e2n_ptr);
     inc->n2e_idx = const_cast<int32_t*>(n2e_idx);
     inc->e2n_idx = const_cast<int32_t*>(e2n_idx);
-    cudaError_t e = cudaMemcpyAsync(inc->h_n2e_ptr.data(), n2e_ptr, ((size_t)num_nodes + 1) * 8,
-                                    cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaMemcpyAsync(inc->h_n2e_ptr.data(), n2e_ptr, ((size_t)num_nodes + 1) * 8,
+                        cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(inc->h_e2n_ptr.data(), e2n_ptr, ((size_t)num_edges + 1) * 8,
                           cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-      hge_set_error("hge_incidence_create: reading row pointers failed: %s", cudaGetErrorString(e));
+      hge_set_error("%s: reading row pointers failed: %s", fn, cudaGetErrorString(e));
       return fail(HGE_ERR_CUDA);
     }
   }
   if (inc->h_n2e_ptr[0] != 0 || inc->h_e2n_ptr[0] != 0) {
-    hge_set_error("hge_incidence_create: row pointers must start at 0");
+    hge_set_error("%s: row pointers must start at 0", fn);
     return fail(HGE_ERR_INVALID);
   }
 
-  // degrees (weights are 1 / degree of the *other* side's row, algebraic_distance.py:47)
-  if ((rc = hge_dev_alloc(ctx, &inc->node_half.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(ctx, &inc->edge_half.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
+  // degrees: a neighbour's weight is 1 / (degree of that neighbour's own row),
+  // algebraic_distance.py:47.  In a shard the edge degrees are the global ones.
+  HgeHalfSchedule& nh = inc->node_half;
+  HgeHalfSchedule& eh = inc->edge_half;
+  nh.ptr = inc->n2e_ptr;
+  nh.idx = inc->n2e_idx;
+  eh.ptr = inc->e2n_ptr;
+  eh.idx = inc->e2n_idx;
+  if ((rc = hge_dev_alloc(ctx, &nh.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
+  if ((rc = hge_dev_alloc(ctx, &eh.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
   k_row_degree<<<grid_1d(ctx, num_nodes, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, inc->n2e_ptr,
-                                                                          inc->node_half.deg);
+                                                                          nh.deg);
   ctx->launches++;
-  k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
-                                                                          inc->edge_half.deg);
-  ctx->launches++;
-  if (cudaGetLastError() != cudaSuccess) {
-    hge_set_error("hge_incidence_create: degree kernel launch failed");
+  if (inc->sharded) {
+    e = cudaMemcpyAsync(eh.deg, edge_deg_global, (size_t)num_edges * 4,
+                        mem == HGE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                        ctx->stream);
+  } else {
+    k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
+                                                                            eh.deg);
+    ctx->launches++;
+  }
+  if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    hge_set_error("%s: degree setup failed", fn);
     return fail(HGE_ERR_CUDA);
   }
-  rc = build_half_schedule(ctx, num_nodes, inc->h_n2e_ptr, inc->n2e_ptr, inc->n2e_idx,
-                           inc->node_half.deg, inc->edge_half.deg, false, "node", &inc->node_half);
+  std::vector<float> h_invs_n, h_invs_e;
+  rc = compute_invs(ctx, num_nodes, inc->n2e_ptr, inc->n2e_idx, eh.deg, &nh.invs, &h_invs_n);
   if (rc != HGE_OK) return fail(rc);
-  rc = build_half_schedule(ctx, num_edges, inc->h_e2n_ptr, inc->e2n_ptr, inc->e2n_idx,
-                           inc->edge_half.deg, inc->node_half.deg, false, "edge", &inc->edge_half);
+  if (inc->sharded) {
+    HGE_REQUIRE(edge_inv_s_global != nullptr, "%s: edge_inv_s_global is NULL", fn);
+    if ((rc = hge_dev_alloc(ctx, &eh.invs, (size_t)num_edges)) != HGE_OK) return fail(rc);
+    h_invs_e.resize((size_t)num_edges);
+    e = cudaMemcpyAsync(eh.invs, edge_inv_s_global, (size_t)num_edges * 4,
+                        mem == HGE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                        ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_invs_e.data(), eh.invs, (size_t)num_edges * 4, cudaMemcpyDeviceToHost,
+                          ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      hge_set_error("%s: edge weight upload failed: %s", fn, cudaGetErrorString(e));
+      return fail(HGE_ERR_CUDA);
+    }
+  } else {
+    rc = compute_invs(ctx, num_edges, inc->e2n_ptr, inc->e2n_idx, nh.deg, &eh.invs, &h_invs_e);
+    if (rc != HGE_OK) return fail(rc);
+  }
+  rc = build_half_schedule(ctx, 0, num_nodes, inc->h_n2e_ptr, h_invs_n, "node", &nh);
   if (rc != HGE_OK) return fail(rc);
+  rc = build_half_schedule(ctx, 0, num_edges, inc->h_e2n_ptr, h_invs_e, "edge", &eh);
+  if (rc != HGE_OK) return fail(rc);
+  if (inc->sharded) {
+    // the sharded edge half runs slice by slice so that the all-reduce of one slice's partial
+    // sums overlaps the gather of the next
+    inc->edge_slices.resize((size_t)num_slices);
+    inc->slice_bounds.resize((size_t)num_slices + 1);
+    for (int k = 0; k <= num_slices; ++k)
+      inc->slice_bounds[(size_t)k] = (int32_t)((int64_t)num_edges * k / num_slices);
+    for (int k = 0; k < num_slices; ++k) {
+      HgeHalfSchedule& sl = inc->edge_slices[(size_t)k];
+      sl.ptr = eh.ptr;
+      sl.idx = eh.idx;
+      sl.deg = eh.deg;
+      sl.invs = eh.invs;
+      rc = build_half_schedule(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
+                               inc->h_e2n_ptr, h_invs_e, "edge", &sl);
+      if (rc != HGE_OK) return fail(rc);
+    }
+  }
   *out = inc;
+  return HGE_OK;
+}
+
+int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
+                         const int64_t* n2e_ptr, const int32_t* n2e_idx,
+                         const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
+                         hge_incidence** out) {
+  return incidence_create_impl(ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
+                               nullptr, nullptr, 1, mem, out);
+}
+
+int hge_incidence_create_sharded(hge_ctx* ctx, int32_t num_local_nodes, int32_t num_edges,
+                                 const int64_t* n2e_ptr, const int32_t* n2e_idx,
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
+                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
+                                 int num_slices, int mem, hge_incidence** out) {
+  HGE_REQUIRE(edge_deg_global != nullptr, "hge_incidence_create_sharded: edge_deg_global is NULL");
+  return incidence_create_impl(ctx, num_local_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
+                               edge_deg_global, edge_inv_s_global, num_slices, mem, out);
+}
+
+int hge_incidence_slice_range(const hge_incidence* inc, int slice, int32_t* row0, int32_t* row1) {
+  HGE_REQUIRE(inc && row0 && row1, "hge_incidence_slice_range: NULL argument");
+  HGE_REQUIRE(inc->sharded && slice >= 0 && slice < (int)inc->edge_slices.size(),
+              "hge_incidence_slice_range: slice %d out of range", slice);
+  *row0 = inc->slice_bounds[(size_t)slice];
+  *row1 = inc->slice_bounds[(size_t)slice + 1];
   return HGE_OK;
 }
 
@@ -791,6 +876,8 @@ int hge_incidence_destroy(hge_incidence* inc) {
   const hge_ctx* ctx = inc->ctx;
   free_half_schedule(ctx, &inc->node_half);
   free_half_schedule(ctx, &inc->edge_half);
+  for (HgeHalfSchedule& sl : inc->edge_slices) free_half_schedule(ctx, &sl, false);
+  inc->edge_slices.clear();
   if (inc->owns_csr) {
     hge_dev_free(ctx, inc->n2e_ptr);
     hge_dev_free(ctx, inc->n2e_idx);
@@ -809,7 +896,7 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   *out = nullptr;
   HGE_REQUIRE(R >= 1 && R <= 1024, "hge_algdist_create: dimension %d not in [1, 1024]", R);
   HGE_REQUIRE(max_iterations >= 0, "hge_algdist_create: negative iteration count");
-  if (inc->node_half.first_empty >= 0 || inc->edge_half.first_empty >= 0) {
+  if (inc->node_half.first_empty >= 0 || (!inc->sharded && inc->edge_half.first_empty >= 0)) {
     const bool node = inc->node_half.first_empty >= 0;
     hge_set_error("%s %d has no incidence: the relaxation divides 0/0 there "
                   "(reference: ZeroDivisionError at algebraic_distance.py:49)",
@@ -839,8 +926,13 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   if ((rc = hge_dev_alloc(ctx, &st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
   if ((rc = hge_dev_alloc(ctx, &st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
     return fail(rc);
-  const size_t n_part = (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials);
-  const size_t n_cnt = (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows) * st->slabs;
+  size_t n_part = (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials);
+  size_t n_cnt = (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows);
+  for (const HgeHalfSchedule& sl : inc->edge_slices) {
+    n_part = std::max(n_part, (size_t)sl.n_partials);
+    n_cnt = std::max(n_cnt, (size_t)sl.n_hrows);
+  }
+  n_cnt *= (size_t)st->slabs;
   if ((rc = hge_dev_alloc(ctx, &st->partials, n_part * st->ld4)) != HGE_OK) return fail(rc);
   if ((rc = hge_dev_alloc(ctx, &st->counters, n_cnt)) != HGE_OK) return fail(rc);
   if (cudaMemsetAsync(st->counters, 0, std::max<size_t>(1, n_cnt) * sizeof(int32_t), ctx->stream) !=
@@ -919,26 +1011,31 @@ int hge_algdist_edge_half(hge_algdist* st, int sweep) {
   return run_half(st, false, sweep, nullptr);
 }
 
-int hge_algdist_edge_partial(hge_algdist* st, int sweep, float* partial) {
+int hge_algdist_edge_partial(hge_algdist* st, int sweep, int slice, float* partial) {
   HGE_REQUIRE(st && partial && sweep >= 0 && sweep < st->max_iters,
               "hge_algdist_edge_partial: bad argument");
+  HGE_REQUIRE(st->inc->sharded && slice >= 0 && slice < (int)st->inc->edge_slices.size(),
+              "hge_algdist_edge_partial: slice %d out of range (sharded incidence needed)", slice);
   HGE_CUDA(cudaSetDevice(st->ctx->device));
-  return run_half(st, false, sweep, partial);
+  return run_half(st, false, sweep, partial, slice);
 }
 
-int hge_algdist_edge_finalize(hge_algdist* st, int sweep, const float* partial,
-                              const float* inv_s_edge_global) {
+int hge_algdist_edge_finalize(hge_algdist* st, int sweep, int slice, const float* partial) {
   HGE_REQUIRE(st && partial && sweep >= 0 && sweep < st->max_iters,
               "hge_algdist_edge_finalize: bad argument");
+  HGE_REQUIRE(st->inc->sharded && slice >= 0 && slice < (int)st->inc->edge_slices.size(),
+              "hge_algdist_edge_finalize: slice %d out of range (sharded incidence needed)", slice);
   HGE_REQUIRE(st->ld <= 1024, "hge_algdist_edge_finalize: dimension too large");
   hge_ctx* ctx = st->ctx;
   hge_incidence* inc = st->inc;
   HGE_CUDA(cudaSetDevice(ctx->device));
   const int32_t* mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
   int32_t* mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
-  const float* invs = inv_s_edge_global ? inv_s_edge_global : inc->edge_half.invs;
-  k_edge_finalize<<<grid_1d(ctx, (int64_t)inc->E * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
-      inc->E, st->R, st->ld, partial, inc->edge_half.deg, invs, mm_prev, mm_cur, st->ye);
+  const int64_t row0 = inc->slice_bounds[(size_t)slice];
+  const int64_t rows = inc->slice_bounds[(size_t)slice + 1] - row0;
+  k_edge_finalize<<<grid_1d(ctx, rows * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
+      row0, rows, st->R, st->ld, partial, inc->edge_half.deg, inc->edge_half.invs, mm_prev, mm_cur,
+      st->ye);
   HGE_CHECK_LAUNCH(ctx);
   return HGE_OK;
 }

@@ -59,5 +59,10 @@ struct hge_incidence {
   int32_t* e2n_idx = nullptr;
   std::vector<int64_t> h_n2e_ptr, h_e2n_ptr;
   HgeHalfSchedule node_half, edge_half;
+  // shard of a row-partitioned hypergraph (hge_incidence_create_sharded): local node rows, all
+  // edges; the edge half is additionally cut into slices of consecutive edges
+  bool sharded = false;
+  std::vector<HgeHalfSchedule> edge_slices;
+  std::vector<int32_t> slice_bounds;
   hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls
 };

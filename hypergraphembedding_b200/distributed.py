@@ -1,0 +1,184 @@
+"""Multi-GPU relaxation: the NODES (and their incidences) are 1-D row-partitioned over the ranks,
+one process per GPU, balanced by incidence count; the E x R edge block is replicated
+(SURVEY.md section 8e).
+
+Per sweep and rank:
+  node half   purely local: gathers the replicated edge rows.
+  edge half   each rank sums  w_n * xn'[n]  over its LOCAL members of every edge
+              (hge_algdist_edge_partial), the partial sums are all-reduced over NVLink
+              (NCCL), and every rank blends / rescales all edge rows redundantly
+              (hge_algdist_edge_finalize).  The edge rows are processed in slices so the
+              all-reduce of slice k runs while slice k+1 is being gathered.
+  rescale     the per-column (min, max) of the sweep -- local nodes + all edges -- is
+              all-reduced (MIN / MAX on order-preserving int32 encodings, 2 x R words).
+One-time set-up collectives: edge degrees (SUM of local counts) and the edges' inverse weight
+sums.  Nothing else crosses GPUs: the 8.3 GB of node rows of config 5 never move.
+
+``ShardedRelaxation`` takes the per-rank kernels as an ``ops`` object; the product default is
+``NativeOps`` (libhge_b200.so).  tests/test_distributed_gloo.py drives the same orchestration
+over ``gloo`` on CPU with a numpy stand-in for the kernels (test infrastructure, not a fallback).
+"""
+import numpy as np
+import scipy.sparse as sps
+
+from . import _native
+
+
+def partition_rows_by_nnz(indptr, parts):
+  """Boundaries b[0..parts] of contiguous row blocks with (almost) equal incidence counts."""
+  indptr = np.asarray(indptr, dtype=np.int64)
+  rows = len(indptr) - 1
+  targets = indptr[-1] * np.arange(1, parts, dtype=np.float64) / parts
+  cuts = np.searchsorted(indptr, targets, side="left")
+  bounds = np.concatenate([[0], np.clip(cuts, 0, rows), [rows]]).astype(np.int64)
+  return np.maximum.accumulate(bounds)
+
+
+def local_shard(node2edges, rank, world):
+  """(A_local, first_row, last_row): this rank's block of node rows of the N x E incidence."""
+  A = sps.csr_matrix(node2edges)
+  bounds = partition_rows_by_nnz(A.indptr, world)
+  r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+  return A[r0:r1], r0, r1
+
+
+class _CudaView(object):
+  """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+
+  def __init__(self, ptr, shape, typestr):
+    self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                     "data": (int(ptr), False), "version": 2}
+
+
+class NativeOps(object):
+  """The per-rank kernels of libhge_b200.so behind the interface ShardedRelaxation drives."""
+
+  def __init__(self, A_local, edge_deg_global, edge_inv_s_global, R, iterations, num_slices,
+               ctx=None, B_local=None):
+    import torch
+    self.torch = torch
+    self.ctx = ctx or _native.default_context()
+    self.device = torch.device("cuda", self.ctx.device)
+    A = sps.csr_matrix(A_local)
+    if B_local is None:
+      B = A.T.tocsr()
+      B.sort_indices()
+    else:
+      B = B_local
+    self.inc = _native.Incidence(self.ctx, A.shape[0], A.shape[1],
+                                 np.asarray(A.indptr, np.int64), np.asarray(A.indices, np.int32),
+                                 np.asarray(B.indptr, np.int64), np.asarray(B.indices, np.int32),
+                                 edge_deg_global=edge_deg_global,
+                                 edge_inv_s_global=edge_inv_s_global, num_slices=num_slices)
+    self.state = _native.AlgDistState(self.ctx, self.inc, R, iterations)
+    self.num_slices = num_slices
+    self.ld = self.state.ld
+    self.num_edges = A.shape[1]
+
+  def new_partial_buffer(self):
+    return self.torch.empty((self.num_edges, self.ld), dtype=self.torch.float32, device=self.device)
+
+  def slice_range(self, k):
+    return self.inc.slice_range(k)
+
+  def load(self, xn, xe):
+    self.state.load(xn, xe)
+
+  def node_half(self, t):
+    self.state.node_half(t)
+
+  def edge_partial(self, t, k, partial):
+    self.state.edge_partial(t, k, partial)
+
+  def edge_finalize(self, t, k, partial):
+    self.state.edge_finalize(t, k, partial)
+
+  def minmax(self, t):
+    """int32 [2, ld] torch view of sweep t's encoded (min, max) slots."""
+    view = _CudaView(self.state.minmax_ptr(t), (2, self.ld), "<i4")
+    return self.torch.as_tensor(view, device=self.device)
+
+  def store(self, sweeps_done, xn, xe):
+    self.state.store(sweeps_done, xn, xe)
+
+  def close(self):
+    self.state.close()
+    self.inc.close()
+
+
+class ShardedRelaxation(object):
+  """Row-partitioned algebraic-distance relaxation over a torch.distributed process group."""
+
+  def __init__(self, A_local, R, iterations, group=None, num_slices=4, ops_factory=None,
+               **ops_kwargs):
+    import torch
+    import torch.distributed as dist
+    self.torch, self.dist, self.group = torch, dist, group
+    self.R, self.iterations = int(R), int(iterations)
+    A = sps.csr_matrix(A_local)
+    self.num_local_nodes, self.num_edges = A.shape
+    num_slices = max(1, min(int(num_slices), self.num_edges))
+    backend = dist.get_backend(group)
+    self.comm_device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" \
+        else torch.device("cpu")
+
+    # one-time collectives: global edge degrees and the edges' inverse weight sums
+    local_deg = np.bincount(A.indices, minlength=self.num_edges).astype(np.int64)
+    node_deg = np.diff(A.indptr).astype(np.float64)
+    if np.any(node_deg == 0):
+      raise ZeroDivisionError("a local node has no incidence (algebraic_distance.py:49)")
+    with np.errstate(divide="ignore"):
+      local_s = np.bincount(A.indices, weights=np.repeat(1.0 / node_deg, np.diff(A.indptr)),
+                            minlength=self.num_edges)
+    deg_t = torch.from_numpy(local_deg).to(self.comm_device)
+    s_t = torch.from_numpy(local_s).to(self.comm_device)
+    dist.all_reduce(deg_t, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(s_t, op=dist.ReduceOp.SUM, group=group)
+    edge_deg = deg_t.cpu().numpy()
+    if np.any(edge_deg == 0):
+      raise ZeroDivisionError("an edge has no incidence on any rank (algebraic_distance.py:49)")
+    self.edge_deg_global = edge_deg.astype(np.int32)
+    self.edge_inv_s_global = (1.0 / s_t.cpu().numpy()).astype(np.float32)
+
+    factory = ops_factory or NativeOps
+    self.ops = factory(A, self.edge_deg_global, self.edge_inv_s_global, self.R, self.iterations,
+                       num_slices, **ops_kwargs)
+    self.num_slices = num_slices
+    self.partial = self.ops.new_partial_buffer()
+
+  def sweep(self, t):
+    self.ops.node_half(t)
+    self.sweep_after_node_half(t)
+
+  def sweep_after_node_half(self, t):
+    dist, ops = self.dist, self.ops
+    pending = []
+    for k in range(self.num_slices):
+      ops.edge_partial(t, k, self.partial)
+      r0, r1 = ops.slice_range(k)
+      # NCCL orders the collective after the partial-sum kernel already queued on this stream
+      # and runs it on its own stream, so it overlaps the next slice's gather
+      pending.append(dist.all_reduce(self.partial[r0:r1], op=dist.ReduceOp.SUM, group=self.group,
+                                     async_op=True))
+    for k in range(self.num_slices):
+      pending[k].wait()
+      ops.edge_finalize(t, k, self.partial)
+    mm = ops.minmax(t)
+    w0 = dist.all_reduce(mm[0], op=dist.ReduceOp.MIN, group=self.group, async_op=True)
+    w1 = dist.all_reduce(mm[1], op=dist.ReduceOp.MAX, group=self.group, async_op=True)
+    w0.wait()
+    w1.wait()
+
+  def run(self, xn_local, xe):
+    """In place: xn_local [n_local, R] (this rank's node rows) and xe [E, R] (replicated, must
+    be identical on every rank)."""
+    if self.iterations == 0:
+      return xn_local, xe
+    self.ops.load(xn_local, xe)
+    for t in range(self.iterations):
+      self.sweep(t)
+    self.ops.store(self.iterations, xn_local, xe)
+    return xn_local, xe
+
+  def close(self):
+    self.ops.close()

@@ -77,6 +77,17 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                          const int64_t* n2e_ptr, const int32_t* n2e_idx,
                          const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
                          hge_incidence** out);
+/* One shard of a hypergraph whose NODES are row-partitioned over several GPUs (DESIGN.md
+ * "Multi-GPU"): n2e holds the num_local_nodes local node rows (global edge ids), e2n holds for
+ * every edge its LOCAL member nodes (local node ids; may be empty).  edge_deg_global[E] and
+ * edge_inv_s_global[E] are the all-reduced edge degrees and 1 / sum_n (1 / deg(n)) over ALL
+ * members.  The edge half-sweep of a shard runs in num_slices slices of consecutive edges. */
+int hge_incidence_create_sharded(hge_ctx* ctx, int32_t num_local_nodes, int32_t num_edges,
+                                 const int64_t* n2e_ptr, const int32_t* n2e_idx,
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
+                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
+                                 int num_slices, int mem, hge_incidence** out);
+int hge_incidence_slice_range(const hge_incidence* inc, int slice, int32_t* row0, int32_t* row1);
 int hge_incidence_destroy(hge_incidence* inc);
 int64_t hge_incidence_nnz(const hge_incidence* inc);
 
@@ -99,12 +110,12 @@ int hge_algdist_destroy(hge_algdist* st);
 int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem);
 int hge_algdist_node_half(hge_algdist* st, int sweep);
 int hge_algdist_edge_half(hge_algdist* st, int sweep);
-/* Sharded edge half: writes the un-normalised local sums  sum_{n local} w_n * xn'[n]  for
- * every edge into partial [E, ld]; after the caller's all-reduce(sum) the second call
- * blends, rescales and stores the edge rows.  ld = hge_algdist_ld(). */
-int hge_algdist_edge_partial(hge_algdist* st, int sweep, float* partial);
-int hge_algdist_edge_finalize(hge_algdist* st, int sweep, const float* partial,
-                              const float* inv_s_edge_global);
+/* Sharded edge half, per slice of edges: the first call writes the un-normalised local sums
+ * sum_{n local} w_n * xn'[n]  of the slice's edges into their rows of partial [E, ld]; after
+ * the caller's all-reduce(sum) of those rows the second call blends, rescales and stores the
+ * slice's edge rows (every shard redundantly).  ld = hge_algdist_ld(). */
+int hge_algdist_edge_partial(hge_algdist* st, int sweep, int slice, float* partial);
+int hge_algdist_edge_finalize(hge_algdist* st, int sweep, int slice, const float* partial);
 /* Device pointer to this sweep's order-preserving int32 encoded (min[ld], max[ld]) slots,
  * for an all-reduce(MIN) / (MAX) across shards. */
 int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out);

@@ -1,0 +1,134 @@
+"""Test infrastructure for the multi-rank relaxation: a numpy stand-in for the per-rank kernels
+(same protocol as hypergraphembedding_b200.distributed.NativeOps: Y rows are kept un-rescaled,
+the previous sweep's affine map is applied lazily, min / max travel as order-preserving int32
+encodings of fp32) and the worker functions the spawn-based tests run."""
+import os
+
+import numpy as np
+import scipy.sparse as sps
+
+
+def enc(x):
+  i = np.asarray(x, dtype=np.float32).view(np.int32)
+  return i ^ ((i >> 31) & 0x7fffffff)
+
+
+def dec(i):
+  i = np.asarray(i, dtype=np.int32)
+  return (i ^ ((i >> 31) & 0x7fffffff)).view(np.float32)
+
+
+class NumpyOps(object):
+
+  def __init__(self, A_local, edge_deg_global, edge_inv_s_global, R, iterations, num_slices):
+    import torch
+    self.torch = torch
+    self.A = sps.csr_matrix(A_local).astype(np.float64)
+    self.B = self.A.T.tocsr()
+    self.w_n = 1.0 / np.diff(self.A.indptr)
+    self.w_e = 1.0 / np.asarray(edge_deg_global, dtype=np.float64)
+    self.inv_s_n = 1.0 / (self.A @ self.w_e)
+    self.inv_s_e = np.asarray(edge_inv_s_global, dtype=np.float64)
+    self.R, self.E = R, self.A.shape[1]
+    self.bounds = [self.E * k // num_slices for k in range(num_slices + 1)]
+    mm = np.empty((max(1, iterations), 2, R), dtype=np.int32)
+    mm[:, 0] = np.iinfo(np.int32).max
+    mm[:, 1] = np.iinfo(np.int32).min
+    self.mm = torch.from_numpy(mm)
+    self.ld = R
+
+  def new_partial_buffer(self):
+    return self.torch.zeros((self.E, self.R), dtype=self.torch.float32)
+
+  def slice_range(self, k):
+    return self.bounds[k], self.bounds[k + 1]
+
+  def load(self, xn, xe):
+    self.xn = np.asarray(xn, dtype=np.float64).copy()
+    self.xe = np.asarray(xe, dtype=np.float64).copy()
+
+  def _affine(self, t):
+    if t == 0:
+      return np.zeros(self.R), np.ones(self.R)
+    m = self.mm[t - 1].numpy()
+    lo, hi = dec(m[0]).astype(np.float64), dec(m[1]).astype(np.float64)
+    return lo, 1.0 / (hi - lo)
+
+  def _track(self, t, x):
+    m = self.mm[t].numpy()
+    m[0] = np.minimum(m[0], enc(x.min(axis=0)))
+    m[1] = np.maximum(m[1], enc(x.max(axis=0)))
+
+  def node_half(self, t):
+    lo, inv = self._affine(t)
+    own = (self.xn - lo) * inv
+    edges = (self.xe - lo) * inv
+    self.xn = 0.5 * (own + (self.A @ (edges * self.w_e[:, None])) * self.inv_s_n[:, None])
+    self._track(t, self.xn)
+
+  def edge_partial(self, t, k, partial):
+    r0, r1 = self.slice_range(k)
+    sums = self.B[r0:r1] @ (self.xn * self.w_n[:, None])
+    partial[r0:r1] = self.torch.from_numpy(sums.astype(np.float32))
+
+  def edge_finalize(self, t, k, partial):
+    r0, r1 = self.slice_range(k)
+    lo, inv = self._affine(t)
+    own = (self.xe[r0:r1] - lo) * inv
+    total = partial[r0:r1].numpy().astype(np.float64)
+    self.xe[r0:r1] = 0.5 * (own + total * self.inv_s_e[r0:r1, None])
+    self._track(t, self.xe[r0:r1])
+
+  def minmax(self, t):
+    return self.mm[t]
+
+  def store(self, sweeps_done, xn, xe):
+    lo, inv = self._affine(sweeps_done)
+    xn[...] = ((self.xn - lo) * inv).astype(xn.dtype)
+    xe[...] = ((self.xe - lo) * inv).astype(xe.dtype)
+
+  def close(self):
+    pass
+
+
+def make_graph(seed, n, e, nnz):
+  rng = np.random.default_rng(seed)
+  rows = np.concatenate([rng.integers(0, n, nnz), np.arange(n), rng.integers(0, n, e)])
+  cols = np.concatenate([rng.integers(0, e, nnz), rng.integers(0, e, n), np.arange(e)])
+  m = sps.csr_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=(n, e), dtype=bool)
+  m.sum_duplicates()
+  m.sort_indices()
+  return m
+
+
+def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, use_native):
+  """Runs the sharded relaxation on one rank and writes its node block to out_dir."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import distributed as hd
+  if use_native:
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+  dist.init_process_group(backend=backend, rank=rank, world_size=world)
+  try:
+    A = make_graph(*graph_args)
+    rng = np.random.default_rng(123)
+    xn0 = rng.random((A.shape[0], R)).astype(np.float32)
+    xe0 = rng.random((A.shape[1], R)).astype(np.float32)
+    A_loc, r0, r1 = hd.local_shard(A, rank, world)
+    relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices,
+                                 ops_factory=None if use_native else NumpyOps)
+    if use_native:
+      xn = torch.from_numpy(xn0[r0:r1].copy()).cuda()
+      xe = torch.from_numpy(xe0.copy()).cuda()
+      relax.run(xn, xe)
+      torch.cuda.synchronize()
+      xn, xe = xn.cpu().numpy(), xe.cpu().numpy()
+    else:
+      xn, xe = xn0[r0:r1].copy(), xe0.copy()
+      relax.run(xn, xe)
+    relax.close()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), xn=xn, xe=xe, r0=r0, r1=r1)
+  finally:
+    dist.destroy_process_group()
