@@ -15,8 +15,11 @@ store) of the BASELINE.json configs[1] workload: synthetic power-law hypergraph,
 `roofline`  the half-sweep kernel: algorithmic bytes per launch / its mean launch
             duration measured with CUDA events on the launch stream, against the measured HBM
             copy peak in MEASURED_PEAKS.json.
-`cpu_baseline` the oracle port (oracle/port.py, scipy f64, one core) on a bounded sample of the
-            same workload, timed on this box's host cores.  Reported, not the target.
+`cpu_baseline` the oracle port (oracle/algdist_ref.c: the reference's per-row f64 arithmetic, all
+            host threads) on the same workload, timed on this box's host cores.  Reported, not
+            the target.
+`hobe`, `pair_weighting`  the other half of BASELINE.json's metric (HOBE weighted samples/s on
+            configs[0]) and the 100M-pair weighting of configs[2].
 """
 import argparse
 import json
@@ -140,46 +143,141 @@ class ClockSampler(object):
             "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_port(A, B, spec, sweeps):
-  """The oracle port on a bounded sample: `sweeps` sweeps of the full workload, scipy f64."""
+def cpu_baseline_port(A, B, spec, sweeps, threads=0):
+  """The oracle port (oracle/algdist_ref.c: the reference's per-row f64 arithmetic, rows spread
+  over all host cores the way the reference spreads them over a process pool) on `sweeps`
+  sweeps of the full workload.  Returns (nnz*R*iters/s, seconds, threads)."""
   from hypergraphembedding_b200 import synthetic
-  from oracle import port
+  from oracle import cport
   xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], spec["R"], seed=0)
+  xn0, xe0 = xn0.astype(np.float64), xe0.astype(np.float64)
+  cport.load()
   t = time.time()
-  port.algdist_vectorised(A, B, xn0, xe0, sweeps)
+  cport.algdist(A, B, xn0, xe0, sweeps, threads=threads)
   dt = time.time() - t
-  return A.nnz * spec["R"] * sweeps / dt, dt
+  return A.nnz * spec["R"] * sweeps / dt, dt, (threads or cport.max_threads())
 
 
 def run_reference(args, spec):
-  """--impl reference: the reference's CPU implementation of the path.  The reference is pure
-  Python and its tree does not travel to the GPU box, so this is the oracle port of it."""
+  """--impl reference: the reference's CPU implementation of the path on this box's host cores.
+  The reference is pure Python (there is nothing of it to compile into oracle/_ref) and its
+  tree does not travel to the GPU box, so this is the oracle port of it: the same per-row f64
+  arithmetic in C, one row block per host thread, every step the full workload."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   A, B = build_workload(spec)
-  sample_sweeps = 2
+  sweeps = spec["sweeps"]
   for _ in range(max(0, min(args.warmup, 1))):
     cpu_baseline_port(A, B, spec, 1)
-  vals, secs = [], []
+  vals, secs, threads = [], [], 1
   for _ in range(max(1, args.steps)):
-    v, dt = cpu_baseline_port(A, B, spec, sample_sweeps)
+    v, dt, threads = cpu_baseline_port(A, B, spec, sweeps)
     vals.append(v)
     secs.append(dt)
-  value = float(np.mean(vals))
-  sample = "%d of %d sweeps of the full workload per step" % (sample_sweeps, spec["sweeps"])
+  value = float(A.nnz * spec["R"] * sweeps * len(secs) / sum(secs))
+  sample = "the full workload (%d sweeps) per step" % sweeps
   out = {
       "impl": "reference", "metric": "alg-dist incidence nnz*R*iters/sec", "value": value,
       "unit": "nnz*R*iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-      "config": {"workload": spec["name"], "nnz": int(A.nnz), "sample": sample},
-      "cpu_baseline": {"value": value, "unit": "nnz*R*iters/s", "cores": 1, "kind": "port",
-                       "sample": sample},
+      "config": {"workload": spec["name"], "nodes": int(A.shape[0]), "edges": int(A.shape[1]),
+                 "nnz": int(A.nnz), "R": spec["R"], "sweeps": sweeps, "seed": spec["seed"]},
+      "cpu_baseline": {"value": value, "unit": "nnz*R*iters/s", "cores": threads, "kind": "port",
+                       "sample": sample, "host_cores": os.cpu_count()},
       "e2e": {"value": value, "unit": "nnz*R*iters/s", "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
   }
   print(json.dumps(out), flush=True)
+
+
+def hobe_extra(ctx):
+  """Second half of BASELINE.json's metric: HOBE weighted samples/s on configs[0] (the youtube
+  fixture, 5 neighbours, 200 samples per row; reference: 1.47e4 samples/s on 8 processes)."""
+  import hypergraphembedding_b200 as H
+  path = os.path.join(ROOT, "tests", "golden", "algdist_youtube.npz")
+  g = np.load(path)
+  node_ids, edge_ids = g["node_ids"], g["edge_ids"]
+  hg = H.Hypergraph()
+  emb = H.HypergraphEmbedding()
+  for n, e in zip(np.searchsorted(node_ids, g["pairs"][:, 0]).tolist(),
+                  np.searchsorted(edge_ids, g["pairs"][:, 1]).tolist()):
+    hg.node[n].edges.append(e)
+    hg.edge[e].nodes.append(n)
+  for i, v in enumerate(g["xn"]):
+    emb.node[i].values.extend(v.tolist())
+  for i, v in enumerate(g["xe"]):
+    emb.edge[i].values.extend(v.tolist())
+  np.random.seed(0)
+  H.AlgebraicDistanceSamples(hg, emb, 5, 20)        # warm-up
+  times = []
+  for _ in range(3):
+    np.random.seed(0)
+    t = time.perf_counter()
+    out = H.AlgebraicDistanceSamples(hg, emb, 5, 200)
+    times.append(time.perf_counter() - t)
+  np.random.seed(0)
+  t = time.perf_counter()
+  fobe = H.BooleanSamples(hg, 5, 200)
+  fobe_s = time.perf_counter() - t
+  return {"workload": "snap_youtube_tiny (3862 nodes / 50 edges / 4548 incidences), R=10, "
+                      "num_neighbors=5, num_samples=200",
+          "records": len(out), "seconds": min(times), "samples_per_s": len(out) / min(times),
+          "unit": "weighted samples/s (proto in, columnar records out)",
+          "fobe_records": len(fobe), "fobe_samples_per_s": len(fobe) / fobe_s}
+
+
+def pair_weighting_extra(ctx, num_pairs=100000000):
+  """BASELINE.json configs[2]: AMiner-shaped bipartite hypergraph, R=64, distance + HOBE weight
+  transform of 100M sampled (node, edge) pairs, everything resident on the device."""
+  import torch
+  from hypergraphembedding_b200 import _native, synthetic
+  from hypergraphembedding_b200 import algebraic_distance as ad
+  t = time.time()
+  A = synthetic.bipartite_author_paper()
+  gen_s = time.time() - t
+  N, E = A.shape
+  R, sweeps = 64, 20
+  xn0, xe0 = synthetic.legacy_initial_vectors(N, E, R, seed=0)
+  inc = ad.make_incidence(A, ctx=ctx)
+  xn, xe = torch.from_numpy(xn0).cuda(), torch.from_numpy(xe0).cuda()
+  init_n, init_e = xn.clone(), xe.clone()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+  _native.algdist_run(ctx, inc, xn, xe, sweeps)
+  xn.copy_(init_n)
+  xe.copy_(init_e)
+  ev[0].record()
+  _native.algdist_run(ctx, inc, xn, xe, sweeps)
+  ev[1].record()
+  coo = A.tocoo()
+  rows = torch.from_numpy(coo.row.astype(np.int32)).cuda()
+  cols = torch.from_numpy(coo.col.astype(np.int32)).cuda()
+  gen = torch.Generator(device="cuda")
+  gen.manual_seed(4321)
+  pick = torch.randint(0, A.nnz, (num_pairs,), device="cuda", generator=gen)
+  ia, ib = rows[pick].contiguous(), cols[pick].contiguous()
+  del pick
+  d = _native.pair_l2(ctx, xn, xe, ia, ib)           # warm-up
+  _native.scale_transform(ctx, d, 0.0)
+  torch.cuda.synchronize()
+  ev[2].record()
+  d = _native.pair_l2(ctx, xn, xe, ia, ib)
+  _native.scale_transform(ctx, d, 0.0)
+  ev[3].record()
+  torch.cuda.synchronize()
+  relax_ms, pair_ms = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+  inc.close()
+  bytes_pair = 8 * R + 12
+  peak, _ = hbm_peak()
+  return {"workload": "AMiner-shaped synthetic bipartite hypergraph %d author nodes / %d paper "
+                      "edges / %d incidences, R=%d" % (N, E, A.nnz, R),
+          "pairs": num_pairs, "pairs_per_s": num_pairs / (pair_ms * 1e-3), "ms": pair_ms,
+          "algorithmic_GBps": num_pairs * bytes_pair / (pair_ms * 1e-3) / 1e9,
+          "frac_of_measured_hbm_peak": num_pairs * bytes_pair / (pair_ms * 1e-3) / 1e9 / peak,
+          "relaxation_ms_20_sweeps": relax_ms,
+          "relaxation_nnz_R_iters_per_s": A.nnz * R * sweeps / (relax_ms * 1e-3),
+          "generate_s": gen_s}
 
 
 def run_ours(args, spec):
@@ -293,8 +391,15 @@ def run_ours(args, spec):
   # parity spot check of what was just timed (device arm vs host arm must agree bit for bit)
   same = bool(np.array_equal(xn.cpu().numpy(), h_xn.numpy()))
 
-  cpu_sweeps = 2
-  cpu_value, cpu_dt = cpu_baseline_port(A, B, spec, cpu_sweeps)
+  cpu_sweeps = sweeps
+  cpu_value, cpu_dt, cpu_threads = cpu_baseline_port(A, B, spec, cpu_sweeps)
+  extras = {}
+  if not args.no_extras:
+    for key, fn in (("hobe", hobe_extra), ("pair_weighting", pair_weighting_extra)):
+      try:
+        extras[key] = fn(ctx)
+      except Exception as exc:   # the headline line must survive a failing side measurement
+        extras[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
   out = {
       "metric": "alg-dist incidence nnz*R*iters/sec", "value": value, "unit": "nnz*R*iters/s",
@@ -311,8 +416,10 @@ def run_ours(args, spec):
                    "bytes_per_launch": bytes_per_launch, "ms_per_launch": mean_half_ms,
                    "node_half_ms": node_ms, "edge_half_ms": edge_ms,
                    "frac_of_nominal_8TBs": achieved / 8000.0},
-      "cpu_baseline": {"value": cpu_value, "unit": "nnz*R*iters/s", "cores": 1, "kind": "port",
-                       "sample": "%d of %d sweeps of the full workload, scipy f64 (%.1f s)"
+      "cpu_baseline": {"value": cpu_value, "unit": "nnz*R*iters/s", "cores": cpu_threads,
+                       "kind": "port",
+                       "sample": "the full workload, %d of %d sweeps, C restatement of the reference's "
+                                 "per-row f64 arithmetic on all host threads (%.1f s)"
                                  % (cpu_sweeps, sweeps, cpu_dt),
                        "host_cores": os.cpu_count()},
       "e2e": {"value": nnz * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
@@ -320,6 +427,7 @@ def run_ours(args, spec):
       "gpu_launches": int(launches),
       "clocks": clocks,
   }
+  out.update(extras)
   print(json.dumps(out), flush=True)
 
 
@@ -459,6 +567,8 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+  ap.add_argument("--no-extras", action="store_true",
+                  help="skip the HOBE samples/s and 100M-pair weighting side measurements")
   ap.add_argument("--slices", type=int, default=4,
                   help="edge slices of the sharded edge half (overlap of all-reduce and gather)")
   args = ap.parse_args()

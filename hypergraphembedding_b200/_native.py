@@ -67,8 +67,10 @@ SIGNATURES = {
     "hge_algdist_edge_partial": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "hge_algdist_edge_finalize": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
     "hge_incidence_create_sharded": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp,
-                                                    c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
-                                                    ctypes.c_int, ctypes.POINTER(c_vp)]),
+                                                    c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.POINTER(c_vp)]),
+    "hge_incidence_edge_sums": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
+    "hge_incidence_finish_sharded": (ctypes.c_int, [c_vp]),
     "hge_incidence_slice_range": (ctypes.c_int, [c_vp, ctypes.c_int, c_i32p, c_i32p]),
     "hge_algdist_minmax_ptr": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "hge_algdist_ld": (ctypes.c_int, [c_vp]),
@@ -225,10 +227,11 @@ def _as_i32(a):
 
 class Incidence(object):
   """Device-resident incidence (hge_incidence): int32 CSR of node->edge and edge->node.  With
-  `edge_deg_global` / `edge_inv_s_global` it is one shard of a node-partitioned hypergraph."""
+  `sharded=True` it is one shard of a node-partitioned hypergraph: all-reduce the arrays
+  returned by `edge_sums()` over the shards, then call `finish_sharded()`."""
 
   def __init__(self, ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
-               edge_deg_global=None, edge_inv_s_global=None, num_slices=1):
+               sharded=False, num_slices=1):
     self.ctx = ctx
     self.num_nodes = int(num_nodes)
     self.num_edges = int(num_edges)
@@ -243,19 +246,16 @@ class Incidence(object):
     self._keep = keep
     handle = c_vp()
     self.num_slices = int(num_slices)
-    if edge_deg_global is None:
+    if not sharded:
       check(ctx.lib.hge_incidence_create(ctx.handle, self.num_nodes, self.num_edges, ptr(keep[0]),
                                          ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
                                          MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)),
             "hge_incidence_create")
     else:
-      if not device:
-        edge_deg_global = _as_i32(edge_deg_global)
-        edge_inv_s_global = np.ascontiguousarray(edge_inv_s_global, dtype=np.float32)
       check(ctx.lib.hge_incidence_create_sharded(
           ctx.handle, self.num_nodes, self.num_edges, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]),
-          ptr(keep[3]), ptr(edge_deg_global), ptr(edge_inv_s_global), self.num_slices,
-          MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)), "hge_incidence_create_sharded")
+          ptr(keep[3]), self.num_slices, MEM_DEVICE if device else MEM_HOST, ctypes.byref(handle)),
+            "hge_incidence_create_sharded")
     self.handle = handle
     self.nnz_n2e = int(keep[1].shape[0])
     self.nnz_e2n = int(keep[3].shape[0])
@@ -268,6 +268,17 @@ class Incidence(object):
 
   def nnz_of(self, order):
     return self.nnz_n2e if order == 0 else self.nnz_e2n
+
+  def edge_sums(self):
+    """(device pointer to int32 [E] local edge degrees, device pointer to f64 [E] local weight
+    sums) of a pending shard; all-reduce both in place, then finish_sharded()."""
+    deg, wsum = c_vp(), c_vp()
+    check(self.ctx.lib.hge_incidence_edge_sums(self.handle, ctypes.byref(deg), ctypes.byref(wsum)),
+          "hge_incidence_edge_sums")
+    return deg.value, wsum.value
+
+  def finish_sharded(self):
+    check(self.ctx.lib.hge_incidence_finish_sharded(self.handle), "hge_incidence_finish_sharded")
 
   def slice_range(self, slice_index):
     r0, r1 = ctypes.c_int32(), ctypes.c_int32()

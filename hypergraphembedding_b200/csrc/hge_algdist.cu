@@ -41,10 +41,10 @@ __global__ void k_row_degree(int32_t rows, const int64_t* __restrict__ ptr,
     deg[r] = (int32_t)(ptr[r + 1] - ptr[r]);
 }
 
-// invs[r] = 1 / sum_{b in row r} 1 / other_deg[b], accumulated in f64 (one warp per row).
-__global__ void k_row_invs(int32_t rows, const int64_t* __restrict__ ptr,
+// wsum[r] = sum_{b in row r} 1 / other_deg[b], accumulated in f64 (one warp per row).
+__global__ void k_row_wsum(int32_t rows, const int64_t* __restrict__ ptr,
                            const int32_t* __restrict__ idx,
-                           const int32_t* __restrict__ other_deg, float* __restrict__ invs) {
+                           const int32_t* __restrict__ other_deg, double* __restrict__ wsum) {
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
@@ -54,8 +54,14 @@ __global__ void k_row_invs(int32_t rows, const int64_t* __restrict__ ptr,
     for (int64_t p = b + lane; p < e; p += 32) s += 1.0 / (double)other_deg[idx[p]];
 #pragma unroll
     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-    if (lane == 0) invs[r] = (float)(1.0 / s);
+    if (lane == 0) wsum[r] = s;
   }
+}
+
+__global__ void k_invert(int32_t rows, const double* __restrict__ wsum, float* __restrict__ invs) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    invs[r] = (float)(1.0 / wsum[r]);
 }
 
 __global__ void k_fill_minmax(int32_t* mm, int slots, int ld) {
@@ -494,12 +500,21 @@ int grid_1d(const hge_ctx* ctx, int64_t work, int block) {
   return (int)std::min(want, cap);
 }
 
-// invs[r] = 1 / sum over the row's neighbours b of 1 / other_deg[b], computed on the device.
-int compute_invs(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, const int32_t* d_idx,
-                 const int32_t* d_other_deg, float** invs, std::vector<float>* h_invs) {
+// wsum[r] = sum over the row's neighbours b of 1 / other_deg[b] (f64, device).
+int compute_wsum(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, const int32_t* d_idx,
+                 const int32_t* d_other_deg, double** wsum) {
+  HGE_TRY(hge_dev_alloc(ctx, wsum, (size_t)rows));
+  k_row_wsum<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
+      rows, d_ptr, d_idx, d_other_deg, *wsum);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
+}
+
+// invs = 1 / wsum as fp32, on the device and mirrored on the host for the work items.
+int invert_wsum(hge_ctx* ctx, int32_t rows, const double* wsum, float** invs,
+                std::vector<float>* h_invs) {
   HGE_TRY(hge_dev_alloc(ctx, invs, (size_t)rows));
-  k_row_invs<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
-      rows, d_ptr, d_idx, d_other_deg, *invs);
+  k_invert<<<grid_1d(ctx, rows, kBlock), kBlock, 0, ctx->stream>>>(rows, wsum, *invs);
   HGE_CHECK_LAUNCH(ctx);
   h_invs->resize((size_t)rows);
   HGE_CUDA(cudaMemcpyAsync(h_invs->data(), *invs, (size_t)rows * sizeof(float),
@@ -694,12 +709,13 @@ int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice =
 
 extern "C" {
 
+static int incidence_finish(hge_incidence* inc);
+
 static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                                  const int64_t* n2e_ptr, const int32_t* n2e_idx,
-                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
-                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx, bool sharded,
                                  int num_slices, int mem, hge_incidence** out) {
-  const char* fn = edge_deg_global ? "hge_incidence_create_sharded" : "hge_incidence_create";
+  const char* fn = sharded ? "hge_incidence_create_sharded" : "hge_incidence_create";
   HGE_REQUIRE(ctx && out, "%s: NULL ctx / out", fn);
   *out = nullptr;
   HGE_REQUIRE(num_nodes > 0 && num_edges > 0, "%s: empty hypergraph (%d nodes, %d edges)", fn,
@@ -715,7 +731,7 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
   inc->ctx = ctx;
   inc->N = num_nodes;
   inc->E = num_edges;
-  inc->sharded = edge_deg_global != nullptr;
+  inc->sharded = sharded;
   int rc = HGE_OK;
   auto fail = [&](int code) {
     hge_incidence_destroy(inc);
@@ -768,76 +784,72 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
   }
 
   // degrees: a neighbour's weight is 1 / (degree of that neighbour's own row),
-  // algebraic_distance.py:47.  In a shard the edge degrees are the global ones.
+  // algebraic_distance.py:47.  In a shard the edge degrees and the edges' weight sums are local
+  // partial values until the caller has all-reduced them (hge_incidence_finish_sharded).
   HgeHalfSchedule& nh = inc->node_half;
   HgeHalfSchedule& eh = inc->edge_half;
   nh.ptr = inc->n2e_ptr;
   nh.idx = inc->n2e_idx;
   eh.ptr = inc->e2n_ptr;
   eh.idx = inc->e2n_idx;
+  inc->num_slices = num_slices;
   if ((rc = hge_dev_alloc(ctx, &nh.deg, (size_t)num_nodes)) != HGE_OK) return fail(rc);
   if ((rc = hge_dev_alloc(ctx, &eh.deg, (size_t)num_edges)) != HGE_OK) return fail(rc);
   k_row_degree<<<grid_1d(ctx, num_nodes, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, inc->n2e_ptr,
                                                                           nh.deg);
   ctx->launches++;
-  if (inc->sharded) {
-    e = cudaMemcpyAsync(eh.deg, edge_deg_global, (size_t)num_edges * 4,
-                        mem == HGE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                        ctx->stream);
-  } else {
-    k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
-                                                                            eh.deg);
-    ctx->launches++;
-  }
-  if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-    hge_set_error("%s: degree setup failed", fn);
+  k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
+                                                                          eh.deg);
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) {
+    hge_set_error("%s: degree kernel launch failed", fn);
     return fail(HGE_ERR_CUDA);
   }
-  std::vector<float> h_invs_n, h_invs_e;
-  rc = compute_invs(ctx, num_nodes, inc->n2e_ptr, inc->n2e_idx, eh.deg, &nh.invs, &h_invs_n);
+  // edge weight sums: sum over (local) members n of 1 / deg(n); node degrees are complete
+  rc = compute_wsum(ctx, num_edges, inc->e2n_ptr, inc->e2n_idx, nh.deg, &inc->edge_wsum);
   if (rc != HGE_OK) return fail(rc);
-  if (inc->sharded) {
-    HGE_REQUIRE(edge_inv_s_global != nullptr, "%s: edge_inv_s_global is NULL", fn);
-    if ((rc = hge_dev_alloc(ctx, &eh.invs, (size_t)num_edges)) != HGE_OK) return fail(rc);
-    h_invs_e.resize((size_t)num_edges);
-    e = cudaMemcpyAsync(eh.invs, edge_inv_s_global, (size_t)num_edges * 4,
-                        mem == HGE_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                        ctx->stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(h_invs_e.data(), eh.invs, (size_t)num_edges * 4, cudaMemcpyDeviceToHost,
-                          ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      hge_set_error("%s: edge weight upload failed: %s", fn, cudaGetErrorString(e));
-      return fail(HGE_ERR_CUDA);
-    }
-  } else {
-    rc = compute_invs(ctx, num_edges, inc->e2n_ptr, inc->e2n_idx, nh.deg, &eh.invs, &h_invs_e);
+  if (!sharded) {
+    rc = incidence_finish(inc);
     if (rc != HGE_OK) return fail(rc);
   }
-  rc = build_half_schedule(ctx, 0, num_nodes, inc->h_n2e_ptr, h_invs_n, "node", &nh);
-  if (rc != HGE_OK) return fail(rc);
-  rc = build_half_schedule(ctx, 0, num_edges, inc->h_e2n_ptr, h_invs_e, "edge", &eh);
-  if (rc != HGE_OK) return fail(rc);
+  *out = inc;
+  return HGE_OK;
+}
+
+// Second phase: edge degrees / weight sums are final (global).  Builds the inverse weight sums
+// and the gather schedules.
+static int incidence_finish(hge_incidence* inc) {
+  hge_ctx* ctx = inc->ctx;
+  HgeHalfSchedule& nh = inc->node_half;
+  HgeHalfSchedule& eh = inc->edge_half;
+  std::vector<float> h_invs_n, h_invs_e;
+  double* node_wsum = nullptr;
+  HGE_TRY(compute_wsum(ctx, inc->N, inc->n2e_ptr, inc->n2e_idx, eh.deg, &node_wsum));
+  int rc = invert_wsum(ctx, inc->N, node_wsum, &nh.invs, &h_invs_n);
+  hge_dev_free(ctx, node_wsum);
+  if (rc != HGE_OK) return rc;
+  HGE_TRY(invert_wsum(ctx, inc->E, inc->edge_wsum, &eh.invs, &h_invs_e));
+  HGE_TRY(build_half_schedule(ctx, 0, inc->N, inc->h_n2e_ptr, h_invs_n, "node", &nh));
+  HGE_TRY(build_half_schedule(ctx, 0, inc->E, inc->h_e2n_ptr, h_invs_e, "edge", &eh));
   if (inc->sharded) {
     // the sharded edge half runs slice by slice so that the all-reduce of one slice's partial
     // sums overlaps the gather of the next
+    const int num_slices = inc->num_slices;
     inc->edge_slices.resize((size_t)num_slices);
     inc->slice_bounds.resize((size_t)num_slices + 1);
     for (int k = 0; k <= num_slices; ++k)
-      inc->slice_bounds[(size_t)k] = (int32_t)((int64_t)num_edges * k / num_slices);
+      inc->slice_bounds[(size_t)k] = (int32_t)((int64_t)inc->E * k / num_slices);
     for (int k = 0; k < num_slices; ++k) {
       HgeHalfSchedule& sl = inc->edge_slices[(size_t)k];
       sl.ptr = eh.ptr;
       sl.idx = eh.idx;
       sl.deg = eh.deg;
       sl.invs = eh.invs;
-      rc = build_half_schedule(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
-                               inc->h_e2n_ptr, h_invs_e, "edge", &sl);
-      if (rc != HGE_OK) return fail(rc);
+      HGE_TRY(build_half_schedule(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
+                                  inc->h_e2n_ptr, h_invs_e, "edge", &sl));
     }
   }
-  *out = inc;
+  inc->finished = true;
   return HGE_OK;
 }
 
@@ -846,17 +858,31 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                          const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,
                          hge_incidence** out) {
   return incidence_create_impl(ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
-                               nullptr, nullptr, 1, mem, out);
+                               false, 1, mem, out);
 }
 
 int hge_incidence_create_sharded(hge_ctx* ctx, int32_t num_local_nodes, int32_t num_edges,
                                  const int64_t* n2e_ptr, const int32_t* n2e_idx,
-                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
-                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
-                                 int num_slices, int mem, hge_incidence** out) {
-  HGE_REQUIRE(edge_deg_global != nullptr, "hge_incidence_create_sharded: edge_deg_global is NULL");
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx, int num_slices,
+                                 int mem, hge_incidence** out) {
   return incidence_create_impl(ctx, num_local_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
-                               edge_deg_global, edge_inv_s_global, num_slices, mem, out);
+                               true, num_slices, mem, out);
+}
+
+int hge_incidence_edge_sums(hge_incidence* inc, int32_t** edge_deg, double** edge_wsum) {
+  HGE_REQUIRE(inc && edge_deg && edge_wsum, "hge_incidence_edge_sums: NULL argument");
+  HGE_REQUIRE(inc->sharded && !inc->finished,
+              "hge_incidence_edge_sums: only valid between create_sharded and finish_sharded");
+  *edge_deg = inc->edge_half.deg;
+  *edge_wsum = inc->edge_wsum;
+  return HGE_OK;
+}
+
+int hge_incidence_finish_sharded(hge_incidence* inc) {
+  HGE_REQUIRE(inc && inc->sharded && !inc->finished,
+              "hge_incidence_finish_sharded: not a pending sharded incidence");
+  HGE_CUDA(cudaSetDevice(inc->ctx->device));
+  return incidence_finish(inc);
 }
 
 int hge_incidence_slice_range(const hge_incidence* inc, int slice, int32_t* row0, int32_t* row1) {
@@ -878,6 +904,7 @@ int hge_incidence_destroy(hge_incidence* inc) {
   free_half_schedule(ctx, &inc->edge_half);
   for (HgeHalfSchedule& sl : inc->edge_slices) free_half_schedule(ctx, &sl, false);
   inc->edge_slices.clear();
+  hge_dev_free(ctx, inc->edge_wsum);
   if (inc->owns_csr) {
     hge_dev_free(ctx, inc->n2e_ptr);
     hge_dev_free(ctx, inc->n2e_idx);
@@ -896,6 +923,7 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   *out = nullptr;
   HGE_REQUIRE(R >= 1 && R <= 1024, "hge_algdist_create: dimension %d not in [1, 1024]", R);
   HGE_REQUIRE(max_iterations >= 0, "hge_algdist_create: negative iteration count");
+  HGE_REQUIRE(inc->finished, "hge_algdist_create: hge_incidence_finish_sharded has not been called");
   if (inc->node_half.first_empty >= 0 || (!inc->sharded && inc->edge_half.first_empty >= 0)) {
     const bool node = inc->node_half.first_empty >= 0;
     hge_set_error("%s %d has no incidence: the relaxation divides 0/0 there "

@@ -62,6 +62,9 @@ struct hge_incidence {
   // shard of a row-partitioned hypergraph (hge_incidence_create_sharded): local node rows, all
   // edges; the edge half is additionally cut into slices of consecutive edges
   bool sharded = false;
+  bool finished = false;           // schedules built (a shard needs the all-reduced edge sums first)
+  int num_slices = 1;
+  double* edge_wsum = nullptr;     // device [E]: sum over members n of 1 / deg(n)
   std::vector<HgeHalfSchedule> edge_slices;
   std::vector<int32_t> slice_bounds;
   hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls

@@ -53,8 +53,7 @@ class _CudaView(object):
 class NativeOps(object):
   """The per-rank kernels of libhge_b200.so behind the interface ShardedRelaxation drives."""
 
-  def __init__(self, A_local, edge_deg_global, edge_inv_s_global, R, iterations, num_slices,
-               ctx=None, B_local=None):
+  def __init__(self, A_local, R, iterations, num_slices, ctx=None, B_local=None):
     import torch
     self.torch = torch
     self.ctx = ctx or _native.default_context()
@@ -65,15 +64,26 @@ class NativeOps(object):
       B.sort_indices()
     else:
       B = B_local
+    self.R, self.iterations = R, iterations
     self.inc = _native.Incidence(self.ctx, A.shape[0], A.shape[1],
                                  np.asarray(A.indptr, np.int64), np.asarray(A.indices, np.int32),
                                  np.asarray(B.indptr, np.int64), np.asarray(B.indices, np.int32),
-                                 edge_deg_global=edge_deg_global,
-                                 edge_inv_s_global=edge_inv_s_global, num_slices=num_slices)
-    self.state = _native.AlgDistState(self.ctx, self.inc, R, iterations)
+                                 sharded=True, num_slices=num_slices)
     self.num_slices = num_slices
-    self.ld = self.state.ld
     self.num_edges = A.shape[1]
+    self.state = None
+
+  def edge_sums(self):
+    """Torch views of the shard's local edge degrees (int32 [E]) and weight sums (f64 [E])."""
+    deg_ptr, wsum_ptr = self.inc.edge_sums()
+    deg = self.torch.as_tensor(_CudaView(deg_ptr, (self.num_edges,), "<i4"), device=self.device)
+    wsum = self.torch.as_tensor(_CudaView(wsum_ptr, (self.num_edges,), "<f8"), device=self.device)
+    return deg, wsum
+
+  def finish(self):
+    self.inc.finish_sharded()
+    self.state = _native.AlgDistState(self.ctx, self.inc, self.R, self.iterations)
+    self.ld = self.state.ld
 
   def new_partial_buffer(self):
     return self.torch.empty((self.num_edges, self.ld), dtype=self.torch.float32, device=self.device)
@@ -102,7 +112,8 @@ class NativeOps(object):
     self.state.store(sweeps_done, xn, xe)
 
   def close(self):
-    self.state.close()
+    if self.state is not None:
+      self.state.close()
     self.inc.close()
 
 
@@ -115,34 +126,19 @@ class ShardedRelaxation(object):
     import torch.distributed as dist
     self.torch, self.dist, self.group = torch, dist, group
     self.R, self.iterations = int(R), int(iterations)
-    A = sps.csr_matrix(A_local)
-    self.num_local_nodes, self.num_edges = A.shape
+    self.num_local_nodes, self.num_edges = A_local.shape
     num_slices = max(1, min(int(num_slices), self.num_edges))
-    backend = dist.get_backend(group)
-    self.comm_device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" \
-        else torch.device("cpu")
-
-    # one-time collectives: global edge degrees and the edges' inverse weight sums
-    local_deg = np.bincount(A.indices, minlength=self.num_edges).astype(np.int64)
-    node_deg = np.diff(A.indptr).astype(np.float64)
-    if np.any(node_deg == 0):
-      raise ZeroDivisionError("a local node has no incidence (algebraic_distance.py:49)")
-    with np.errstate(divide="ignore"):
-      local_s = np.bincount(A.indices, weights=np.repeat(1.0 / node_deg, np.diff(A.indptr)),
-                            minlength=self.num_edges)
-    deg_t = torch.from_numpy(local_deg).to(self.comm_device)
-    s_t = torch.from_numpy(local_s).to(self.comm_device)
-    dist.all_reduce(deg_t, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(s_t, op=dist.ReduceOp.SUM, group=group)
-    edge_deg = deg_t.cpu().numpy()
-    if np.any(edge_deg == 0):
-      raise ZeroDivisionError("an edge has no incidence on any rank (algebraic_distance.py:49)")
-    self.edge_deg_global = edge_deg.astype(np.int32)
-    self.edge_inv_s_global = (1.0 / s_t.cpu().numpy()).astype(np.float32)
-
     factory = ops_factory or NativeOps
-    self.ops = factory(A, self.edge_deg_global, self.edge_inv_s_global, self.R, self.iterations,
-                       num_slices, **ops_kwargs)
+    self.ops = factory(A_local, self.R, self.iterations, num_slices, **ops_kwargs)
+    # the one set-up exchange: global edge degrees and the edges' weight sums
+    deg, wsum = self.ops.edge_sums()
+    w0 = dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w1 = dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w0.wait()
+    w1.wait()
+    if bool((deg == 0).any()):
+      raise ZeroDivisionError("an edge has no incidence on any rank (algebraic_distance.py:49)")
+    self.ops.finish()
     self.num_slices = num_slices
     self.partial = self.ops.new_partial_buffer()
 

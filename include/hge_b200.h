@@ -79,14 +79,20 @@ int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                          hge_incidence** out);
 /* One shard of a hypergraph whose NODES are row-partitioned over several GPUs (DESIGN.md
  * "Multi-GPU"): n2e holds the num_local_nodes local node rows (global edge ids), e2n holds for
- * every edge its LOCAL member nodes (local node ids; may be empty).  edge_deg_global[E] and
- * edge_inv_s_global[E] are the all-reduced edge degrees and 1 / sum_n (1 / deg(n)) over ALL
- * members.  The edge half-sweep of a shard runs in num_slices slices of consecutive edges. */
+ * every edge its LOCAL member nodes (local node ids; may be empty).  Creation is two-phase:
+ *   1. hge_incidence_create_sharded uploads the arrays and computes, on the device, the local
+ *      edge degrees (int32 [E]) and the local edge weight sums  sum_{n local} 1 / deg(n)
+ *      (f64 [E]);
+ *   2. the caller all-reduces (SUM) both arrays in place through the device pointers returned
+ *      by hge_incidence_edge_sums -- the one set-up exchange of the path --
+ *   3. hge_incidence_finish_sharded builds the inverse weight sums and the gather schedules.
+ * The edge half-sweep of a shard runs in num_slices slices of consecutive edges. */
 int hge_incidence_create_sharded(hge_ctx* ctx, int32_t num_local_nodes, int32_t num_edges,
                                  const int64_t* n2e_ptr, const int32_t* n2e_idx,
-                                 const int64_t* e2n_ptr, const int32_t* e2n_idx,
-                                 const int32_t* edge_deg_global, const float* edge_inv_s_global,
-                                 int num_slices, int mem, hge_incidence** out);
+                                 const int64_t* e2n_ptr, const int32_t* e2n_idx, int num_slices,
+                                 int mem, hge_incidence** out);
+int hge_incidence_edge_sums(hge_incidence* inc, int32_t** edge_deg, double** edge_wsum);
+int hge_incidence_finish_sharded(hge_incidence* inc);
 int hge_incidence_slice_range(const hge_incidence* inc, int slice, int32_t* row0, int32_t* row1);
 int hge_incidence_destroy(hge_incidence* inc);
 int64_t hge_incidence_nnz(const hge_incidence* inc);

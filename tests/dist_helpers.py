@@ -20,22 +20,33 @@ def dec(i):
 
 class NumpyOps(object):
 
-  def __init__(self, A_local, edge_deg_global, edge_inv_s_global, R, iterations, num_slices):
+  def __init__(self, A_local, R, iterations, num_slices):
     import torch
     self.torch = torch
     self.A = sps.csr_matrix(A_local).astype(np.float64)
     self.B = self.A.T.tocsr()
-    self.w_n = 1.0 / np.diff(self.A.indptr)
-    self.w_e = 1.0 / np.asarray(edge_deg_global, dtype=np.float64)
-    self.inv_s_n = 1.0 / (self.A @ self.w_e)
-    self.inv_s_e = np.asarray(edge_inv_s_global, dtype=np.float64)
+    node_deg = np.diff(self.A.indptr)
+    if np.any(node_deg == 0):
+      raise ZeroDivisionError("a local node has no incidence")
+    self.w_n = 1.0 / node_deg
     self.R, self.E = R, self.A.shape[1]
+    self.iterations = iterations
     self.bounds = [self.E * k // num_slices for k in range(num_slices + 1)]
-    mm = np.empty((max(1, iterations), 2, R), dtype=np.int32)
+    self.ld = R
+    self._deg = torch.from_numpy(np.diff(self.B.indptr).astype(np.int32))
+    self._wsum = torch.from_numpy(np.asarray(self.B @ self.w_n, dtype=np.float64))
+
+  def edge_sums(self):
+    return self._deg, self._wsum
+
+  def finish(self):
+    self.w_e = 1.0 / self._deg.numpy().astype(np.float64)
+    self.inv_s_n = 1.0 / (self.A @ self.w_e)
+    self.inv_s_e = (1.0 / self._wsum.numpy()).astype(np.float32).astype(np.float64)
+    mm = np.empty((max(1, self.iterations), 2, self.R), dtype=np.int32)
     mm[:, 0] = np.iinfo(np.int32).max
     mm[:, 1] = np.iinfo(np.int32).min
-    self.mm = torch.from_numpy(mm)
-    self.ld = R
+    self.mm = self.torch.from_numpy(mm)
 
   def new_partial_buffer(self):
     return self.torch.zeros((self.E, self.R), dtype=self.torch.float32)

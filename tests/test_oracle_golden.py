@@ -161,3 +161,21 @@ def test_lifo_rows_and_rng_replay_match_scipy_and_numpy():
   assert got == tuple(want)
   st, st2 = rp.state_tuple(), np.random.get_state()
   assert (st[1] == st2[1]).all() and st[2] == st2[2]
+
+
+@pytest.mark.parametrize("name", ["tiny", "rand25", "youtube"])
+def test_c_restatement_reproduces_the_reference_bit_for_bit(name):
+  """oracle/algdist_ref.c (bench.py's cpu_baseline / --impl reference) performs the reference's
+  f64 operations in the reference's order: after the fp32 store its output is identical to the
+  unmodified reference's, for 1 thread and for all threads."""
+  from oracle import cport
+  g = load_golden("algdist_" + name)
+  A = _compressed_csr(g)
+  B = A.T.tocsr()
+  B.sort_indices()
+  np.random.seed(int(g["seed"]))
+  xn0, xe0 = port.algdist_init(A.shape[0], A.shape[1], int(g["dim"]))
+  for threads in (1, 0):
+    xn, xe = cport.algdist(A, B, xn0, xe0, int(g["iters"]), threads=threads)
+    assert np.array_equal(xn.astype(np.float32), g["xn"])
+    assert np.array_equal(xe.astype(np.float32), g["xe"])
