@@ -440,9 +440,13 @@ def run_sharded(args, spec, world, rank, local_rank):
   from hypergraphembedding_b200 import distributed as hd
 
   torch.cuda.set_device(local_rank)
+  if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout (one JSON line)
   dist.init_process_group(backend="nccl", rank=rank, world_size=world,
                           device_id=torch.device("cuda", local_rank))
   ctx = _native.default_context(local_rank)
+  if os.environ.get("HGE_BLOCKS_PER_SM"):
+    ctx.set_tuning(0, 0, int(os.environ["HGE_BLOCKS_PER_SM"]))
   shard_spec = dict(spec, seed=spec["seed"] + rank)
   A, B = build_workload(shard_spec)
   n_loc, E = A.shape
