@@ -461,7 +461,9 @@ def run_sharded(args, spec, world, rank, local_rank):
   xn0, xe0 = synthetic.legacy_initial_vectors(n_loc, E, R, seed=rank)
   xe0 = synthetic.legacy_initial_vectors(1, E, R, seed=10**6)[1]     # identical on every rank
 
-  relax = hd.ShardedRelaxation(A, R, sweeps, num_slices=args.slices, ctx=ctx, B_local=B)
+  relax = hd.ShardedRelaxation(A, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
+                               B_local=B)
+  comm = "p2p" if relax.use_p2p else "nccl"
   xn_init, xe_init = torch.from_numpy(xn0).cuda(), torch.from_numpy(xe0).cuda()
   xn, xe = torch.empty_like(xn_init), torch.empty_like(xe_init)
 
@@ -493,20 +495,31 @@ def run_sharded(args, spec, world, rank, local_rank):
   ms_per_step = total_ms / args.steps
   value = nnz_global * R * sweeps / (ms_per_step * 1e-3)
 
-  # per-launch time of the node half-sweep kernel on this rank (it is the same kernel and the
-  # same shard shape as at N = 1)
-  evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * sweeps)]
+  # per-sweep device time on this rank; with the NCCL exchange also the node half-sweep launch
+  # alone (the same kernel and shard shape as at N = 1)
+  evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * sweeps + 1)]
   relax.ops.load(xn_init, xe_init)
   for t in range(sweeps):
     evs[2 * t].record()
-    relax.ops.node_half(t)
-    evs[2 * t + 1].record()
-    relax.sweep_after_node_half(t)
+    if relax.use_p2p:
+      relax.sweep(t)
+    else:
+      relax.ops.node_half(t)
+      evs[2 * t + 1].record()
+      relax.sweep_after_node_half(t)
+  evs[2 * sweeps].record()
   torch.cuda.synchronize()
-  node_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 1]) for t in range(sweeps)]))
-  bytes_node = nnz_local * (4 * R + 4) + 2 * n_loc * 4 * R
-  achieved = bytes_node / (node_ms * 1e-3) / 1e9
+  sweep_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 2]) for t in range(sweeps)]))
   peak, peak_src = hbm_peak()
+  if relax.use_p2p:
+    kernel = "fused sweep: k_half_sweep<8> node half + edge gather with peer push + k_edge_reduce_push + 2 flag barriers (rank 0)"
+    bytes_launch = algorithmic_bytes_per_sweep(n_loc, E, nnz_local, R)
+    launch_ms = sweep_ms
+  else:
+    kernel = "k_half_sweep<8> (node half, rank 0)"
+    bytes_launch = nnz_local * (4 * R + 4) + 2 * n_loc * 4 * R
+    launch_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 1]) for t in range(sweeps)]))
+  achieved = bytes_launch / (launch_ms * 1e-3) / 1e9
 
   # end to end: host buffers in, host buffers out, incidence upload and set-up collectives inside
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -514,7 +527,8 @@ def run_sharded(args, spec, world, rank, local_rank):
   h_xn, h_xe = pin(np.empty_like(xn0)), pin(np.empty_like(xe0))
 
   def step_host():
-    r = hd.ShardedRelaxation(A, R, sweeps, num_slices=args.slices, ctx=ctx, B_local=B)
+    r = hd.ShardedRelaxation(A, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
+                             B_local=B)
     r.run(h_xn.numpy(), h_xe.numpy())
     r.close()
 
@@ -548,14 +562,18 @@ def run_sharded(args, spec, world, rank, local_rank):
         "config": {"workload": "%d x [%s] node blocks over the same %d edges" % (world, spec["name"], E),
                    "nodes": n_loc * world, "edges": E, "nnz": nnz_global, "nnz_per_gpu": nnz_local,
                    "R": R, "sweeps": sweeps, "seed": spec["seed"], "slices": args.slices,
-                   "partition": "nodes row-partitioned, edge block replicated; per sweep: all-reduce(sum) "
-                                "of E x R partial sums in slices + all-reduce(min/max) of 2R bounds (NCCL)",
+                   "exchange": comm,
+                   "partition": "nodes row-partitioned, edge block replicated; per sweep: reduce-scatter of "
+                                "the E x R partial sums to the owning GPU, all-gather of the updated edge "
+                                "rows, all-reduce(min/max) of 2R bounds -- " +
+                                ("stores to peer memory from inside the kernels + flag barriers"
+                                 if comm == "p2p" else "NCCL all-reduce between the kernels"),
                    "l2": "no flush: per-GPU working set exceeds the 126 MB L2",
                    "device_vs_host_arm_identical": same},
-        "roofline": {"bound": "hbm", "kernel": "k_half_sweep<8> (node half, rank 0)",
+        "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_node,
-                     "ms_per_launch": node_ms},
+                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_launch,
+                     "ms_per_launch": launch_ms, "ms_per_sweep": sweep_ms},
         "cpu_baseline": None,
         "e2e": {"value": nnz_global * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
                 "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * world,
@@ -576,7 +594,9 @@ def main():
   ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
   ap.add_argument("--no-extras", action="store_true",
                   help="skip the HOBE samples/s and 100M-pair weighting side measurements")
-  ap.add_argument("--slices", type=int, default=4,
+  ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
+                  help="exchange of the sharded edge half: peer-memory stores inside the kernels, or NCCL")
+  ap.add_argument("--slices", type=int, default=1,
                   help="edge slices of the sharded edge half (overlap of all-reduce and gather)")
   args = ap.parse_args()
   spec = WORKLOADS[args.workload]

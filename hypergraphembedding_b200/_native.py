@@ -75,6 +75,15 @@ SIGNATURES = {
     "hge_algdist_minmax_ptr": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "hge_algdist_ld": (ctypes.c_int, [c_vp]),
     "hge_algdist_store": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int]),
+    "hge_p2p_create": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int32, ctypes.c_int,
+                                      ctypes.POINTER(c_vp)]),
+    "hge_p2p_export": (ctypes.c_int, [c_vp, c_vp]),
+    "hge_p2p_open_peers": (ctypes.c_int, [c_vp, c_vp]),
+    "hge_p2p_check": (ctypes.c_int, [c_vp]),
+    "hge_p2p_close_peers": (ctypes.c_int, [c_vp]),
+    "hge_p2p_destroy": (ctypes.c_int, [c_vp]),
+    "hge_algdist_attach_p2p": (ctypes.c_int, [c_vp, c_vp]),
+    "hge_algdist_sweep_p2p": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "hge_incidence_l2": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, c_vp, ctypes.c_int]),
     "hge_pair_l2": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int,
@@ -342,6 +351,12 @@ class AlgDistState(object):
     check(self.ctx.lib.hge_algdist_edge_finalize(self.handle, sweep, slice_index, ptr(partial)),
           "hge_algdist_edge_finalize")
 
+  def attach_p2p(self, arena):
+    check(self.ctx.lib.hge_algdist_attach_p2p(self.handle, arena.handle), "hge_algdist_attach_p2p")
+
+  def sweep_p2p(self, sweep):
+    check(self.ctx.lib.hge_algdist_sweep_p2p(self.handle, sweep), "hge_algdist_sweep_p2p")
+
   def minmax_ptr(self, sweep):
     out = c_vp()
     check(self.ctx.lib.hge_algdist_minmax_ptr(self.handle, sweep, ctypes.byref(out)))
@@ -540,3 +555,36 @@ def sample_neighbors(n2e, e2n, nodes, edges, k, state):
     raise ValueError("'a' cannot be empty unless no samples are taken")
   check(rc, "hge_sample_neighbors")
   return nbr_e, nbr_n
+
+
+class PeerArena(object):
+  """hge_p2p: the IPC-shared exchange arena of one shard."""
+
+  def __init__(self, ctx, rank, world, num_edges, ld):
+    self.ctx = ctx
+    handle = c_vp()
+    check(ctx.lib.hge_p2p_create(ctx.handle, rank, world, num_edges, ld, ctypes.byref(handle)),
+          "hge_p2p_create")
+    self.handle = handle
+    self.world = world
+
+  def export(self):
+    buf = np.zeros(64, dtype=np.uint8)
+    check(self.ctx.lib.hge_p2p_export(self.handle, ptr(buf)), "hge_p2p_export")
+    return buf
+
+  def open_peers(self, handles):
+    handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(self.world, 64)
+    check(self.ctx.lib.hge_p2p_open_peers(self.handle, ptr(handles)), "hge_p2p_open_peers")
+
+  def check(self):
+    check(self.ctx.lib.hge_p2p_check(self.handle), "hge_p2p_check")
+
+  def close_peers(self):
+    if getattr(self, "handle", None):
+      self.ctx.lib.hge_p2p_close_peers(self.handle)
+
+  def close(self):
+    if getattr(self, "handle", None):
+      self.ctx.lib.hge_p2p_destroy(self.handle)
+      self.handle = None

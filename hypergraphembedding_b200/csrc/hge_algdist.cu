@@ -125,6 +125,11 @@ struct HalfSweepArgs {
   int32_t gather_affine;       // 1: gathered rows carry the previous sweep's affine (node half)
   int32_t raw_out;             // 1: write the raw gathered sums to raw[rows, ld4] (sharded edge half)
   float4* raw;
+  // raw_out == 2: peer-memory push.  Row r belongs to rank r / push_rows; its raw sums go to
+  // that rank's staging block  push_stage[owner] + (push_rank * push_rows + r % push_rows) rows
+  float4* const* push_stage;
+  int32_t push_rows;
+  int32_t push_rank;
   int32_t R;
   int32_t ld4;
 };
@@ -252,7 +257,16 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
     // called by the lanes that own (row, c4); acc is the full gathered sum
     const size_t off = (size_t)row * ld4 + c4;
     if (raw_out) {
-      a.raw[off] = acc;
+      if (a.raw_out == 2) {
+        // fused reduce-scatter: the partial row is stored straight into the owning GPU's
+        // staging block over NVLink (one 128-byte line per sub-warp, posted write)
+        const int owner = row / a.push_rows;
+        float4* dst = a.push_stage[owner] +
+                      ((size_t)a.push_rank * a.push_rows + (row - owner * a.push_rows)) * ld4 + c4;
+        *dst = acc;
+      } else {
+        a.raw[off] = acc;
+      }
       return;
     }
     const float4 x = finalize_value(yown, acc, degf, invs, af, gaff);
@@ -636,21 +650,6 @@ void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays
 // relaxation state
 // ----------------------------------------------------------------------------------------
 
-struct hge_algdist {
-  hge_ctx* ctx = nullptr;
-  hge_incidence* inc = nullptr;
-  int R = 0, ld = 0, ld4 = 0, lpr = 0, slabs = 1;
-  int max_iters = 0;
-  float* yn = nullptr;
-  float* ye = nullptr;
-  int32_t* mm = nullptr;        // [max_iters][2][ld]
-  float4* partials = nullptr;   // max over the two halves
-  int32_t* counters = nullptr;
-  float* stage_n = nullptr;     // host-call staging (dense [N, R] / [E, R])
-  float* stage_e = nullptr;
-  int grid = 0;
-};
-
 namespace {
 
 template <int LPR>
@@ -671,7 +670,8 @@ int occupancy_grid(const hge_ctx* ctx, int* out) {
   return HGE_OK;
 }
 
-int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice = -1) {
+int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice = -1,
+             const hge_p2p* push = nullptr) {
   hge_incidence* inc = st->inc;
   const HgeHalfSchedule& s = node_half ? inc->node_half
                                        : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
@@ -691,8 +691,11 @@ int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice =
   a.mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
   a.mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
   a.gather_affine = node_half ? 1 : 0;
-  a.raw_out = raw ? 1 : 0;
+  a.raw_out = push ? 2 : (raw ? 1 : 0);
   a.raw = reinterpret_cast<float4*>(raw);
+  a.push_stage = push ? push->d_peer_stage : nullptr;
+  a.push_rows = push ? push->own_rows : 1;
+  a.push_rank = push ? push->rank : 0;
   a.R = st->R;
   a.ld4 = st->ld4;
   switch (st->lpr) {
@@ -986,7 +989,7 @@ int hge_algdist_destroy(hge_algdist* st) {
   cudaSetDevice(st->ctx->device);
   const hge_ctx* ctx = st->ctx;
   hge_dev_free(ctx, st->yn);
-  hge_dev_free(ctx, st->ye);
+  if (st->owns_ye) hge_dev_free(ctx, st->ye);
   hge_dev_free(ctx, st->mm);
   hge_dev_free(ctx, st->partials);
   hge_dev_free(ctx, st->counters);
@@ -1066,6 +1069,10 @@ int hge_algdist_edge_finalize(hge_algdist* st, int sweep, int slice, const float
       st->ye);
   HGE_CHECK_LAUNCH(ctx);
   return HGE_OK;
+}
+
+int hge_internal_edge_push(hge_algdist* st, int sweep) {
+  return run_half(st, false, sweep, nullptr, -1, st->p2p);
 }
 
 int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out) {

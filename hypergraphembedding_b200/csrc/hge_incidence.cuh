@@ -69,3 +69,42 @@ struct hge_incidence {
   std::vector<int32_t> slice_bounds;
   hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls
 };
+
+// Peer-memory exchange arena of one shard (csrc/hge_p2p.cu): one cudaMalloc block, exported to
+// the other ranks of the node through CUDA IPC.
+struct hge_p2p {
+  hge_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  int32_t E = 0, ld = 0, own_rows = 0;      // own_rows = ceil(E / world)
+  char* base = nullptr;                      // local arena
+  size_t off_ye = 0, off_stage = 0, off_mmx = 0, off_flags = 0, off_err = 0, bytes = 0;
+  char* peer_base[16] = {nullptr};           // peer arenas (own slot = base)
+  // device-side pointer tables [world]
+  float4** d_peer_stage = nullptr;
+  float4** d_peer_ye = nullptr;
+  int32_t** d_peer_mmx = nullptr;
+  uint32_t** d_peer_flags = nullptr;
+  uint32_t seq = 0;                          // barrier sequence number (same on every rank)
+  bool peers_open = false;
+};
+
+// Relaxation state (csrc/hge_algdist.cu).
+struct hge_algdist {
+  hge_ctx* ctx = nullptr;
+  hge_incidence* inc = nullptr;
+  int R = 0, ld = 0, ld4 = 0, lpr = 0, slabs = 1;
+  int max_iters = 0;
+  float* yn = nullptr;
+  float* ye = nullptr;
+  bool owns_ye = true;          // false: ye lives in a peer-memory arena
+  int32_t* mm = nullptr;        // [max_iters][2][ld]
+  float4* partials = nullptr;   // max over the two halves
+  int32_t* counters = nullptr;
+  float* stage_n = nullptr;     // host-call staging (dense [N, R] / [E, R])
+  float* stage_e = nullptr;
+  int grid = 0;
+  hge_p2p* p2p = nullptr;
+};
+
+// internal: the sharded edge gather with the partial rows pushed to their owners
+extern "C" int hge_internal_edge_push(hge_algdist* st, int sweep);

@@ -111,21 +111,51 @@ class NativeOps(object):
   def store(self, sweeps_done, xn, xe):
     self.state.store(sweeps_done, xn, xe)
 
+  # ---- peer-memory exchange (csrc/hge_p2p.cu) ------------------------------------------
+  def enable_p2p(self, dist, group):
+    """Creates this rank's exchange arena, swaps the 64-byte IPC handles with the other ranks
+    and attaches the arena to the relaxation state."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    self.arena = _native.PeerArena(self.ctx, rank, world, self.num_edges, self.ld)
+    mine = self.torch.from_numpy(self.arena.export()).to(self.device)
+    every = [self.torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    self.arena.open_peers(self.torch.stack(every).cpu().numpy())
+    self.state.attach_p2p(self.arena)
+    self._dist, self._group = dist, group
+    dist.barrier(group=group)
+
+  def sweep_p2p(self, t):
+    self.state.sweep_p2p(t)
+
+  def check_p2p(self):
+    self.arena.check()
+
   def close(self):
+    arena = getattr(self, "arena", None)
+    if arena is not None:
+      # nobody may free an arena a peer still has mapped or is still writing to
+      self.ctx.sync()
+      self._dist.barrier(group=self._group)
+      arena.close_peers()
+      self._dist.barrier(group=self._group)
     if self.state is not None:
       self.state.close()
+    if arena is not None:
+      arena.close()
     self.inc.close()
 
 
 class ShardedRelaxation(object):
   """Row-partitioned algebraic-distance relaxation over a torch.distributed process group."""
 
-  def __init__(self, A_local, R, iterations, group=None, num_slices=4, ops_factory=None,
-               **ops_kwargs):
+  def __init__(self, A_local, R, iterations, group=None, num_slices=1, ops_factory=None,
+               comm="auto", **ops_kwargs):
     import torch
     import torch.distributed as dist
     self.torch, self.dist, self.group = torch, dist, group
     self.R, self.iterations = int(R), int(iterations)
+    self.check_barriers = True
     self.num_local_nodes, self.num_edges = A_local.shape
     num_slices = max(1, min(int(num_slices), self.num_edges))
     factory = ops_factory or NativeOps
@@ -140,9 +170,33 @@ class ShardedRelaxation(object):
       raise ZeroDivisionError("an edge has no incidence on any rank (algebraic_distance.py:49)")
     self.ops.finish()
     self.num_slices = num_slices
-    self.partial = self.ops.new_partial_buffer()
+    # exchange strategy: "p2p" = fused into the kernels over peer memory (one node, one GPU
+    # per rank), "nccl" = host-interleaved NCCL / gloo collectives
+    assert comm in ("auto", "p2p", "nccl")
+    can_p2p = hasattr(self.ops, "enable_p2p") and dist.get_backend(group) == "nccl" and \
+        self._one_gpu_per_rank_on_one_node()
+    if comm == "p2p" and not can_p2p:
+      raise RuntimeError("peer-memory exchange needs NCCL ranks on distinct GPUs of one node")
+    self.use_p2p = can_p2p and comm in ("auto", "p2p")
+    if self.use_p2p:
+      self.ops.enable_p2p(dist, group)
+      self.partial = None
+    else:
+      self.partial = self.ops.new_partial_buffer()
+
+  def _one_gpu_per_rank_on_one_node(self):
+    import socket
+    torch, dist = self.torch, self.dist
+    props = torch.cuda.get_device_properties(torch.cuda.current_device())
+    mine = (socket.gethostname(), str(getattr(props, "uuid", torch.cuda.current_device())))
+    every = [None] * dist.get_world_size(self.group)
+    dist.all_gather_object(every, mine, group=self.group)
+    return len({h for h, _ in every}) == 1 and len({u for _, u in every}) == len(every)
 
   def sweep(self, t):
+    if self.use_p2p:
+      self.ops.sweep_p2p(t)
+      return
     self.ops.node_half(t)
     self.sweep_after_node_half(t)
 
@@ -174,6 +228,8 @@ class ShardedRelaxation(object):
     for t in range(self.iterations):
       self.sweep(t)
     self.ops.store(self.iterations, xn_local, xe)
+    if self.use_p2p and self.check_barriers:
+      self.ops.check_p2p()
     return xn_local, xe
 
   def close(self):

@@ -128,6 +128,27 @@ int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out);
 int hge_algdist_ld(const hge_algdist* st);
 int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, int mem);
 
+/* ---- peer-memory exchange for the sharded relaxation (single node, NVLink) ---------------
+ * The collectives of the sharded edge half done by the kernels themselves: partial rows are
+ * stored into the owning GPU's staging block from inside the gather kernel (reduce-scatter),
+ * the owner reduces them in rank order, updates the edge rows and stores them into every
+ * rank's edge block (all-gather); barriers and the min / max exchange are flags and 2R-word
+ * slots in peer memory.  One arena per rank, shared through CUDA IPC: create, export the
+ * 64-byte handle, exchange the handles between the ranks (any transport), open the peers'
+ * arenas, attach to the relaxation state; then hge_algdist_sweep_p2p replaces
+ * node_half / edge_partial / all-reduce / edge_finalize / min-max all-reduce.  All ranks must
+ * call the same sequence of sweeps; each rank must drive its own GPU.  A barrier that is not
+ * met within 20 s raises an error flag (hge_p2p_check) instead of hanging. */
+typedef struct hge_p2p hge_p2p;
+int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_edges, int ld, hge_p2p** out);
+int hge_p2p_export(hge_p2p* p, void* handle64);
+int hge_p2p_open_peers(hge_p2p* p, const void* handles /* world x 64 bytes */);
+int hge_p2p_check(hge_p2p* p);
+int hge_p2p_close_peers(hge_p2p* p);   /* all ranks, then a host barrier, then destroy */
+int hge_p2p_destroy(hge_p2p* p);
+int hge_algdist_attach_p2p(hge_algdist* st, hge_p2p* p);
+int hge_algdist_sweep_p2p(hge_algdist* st, int sweep);
+
 /* ---- distances and HOBE / FOBE weights ------------------------------------------------
  * All vectors are dense fp32 [rows, R]; outputs are fp32.  `mem` applies to every array
  * argument of a call. */

@@ -112,7 +112,8 @@ def make_graph(seed, n, e, nnz):
   return m
 
 
-def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, use_native):
+def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, use_native,
+           comm="nccl"):
   """Runs the sharded relaxation on one rank and writes its node block to out_dir."""
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
@@ -128,8 +129,9 @@ def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, us
     xn0 = rng.random((A.shape[0], R)).astype(np.float32)
     xe0 = rng.random((A.shape[1], R)).astype(np.float32)
     A_loc, r0, r1 = hd.local_shard(A, rank, world)
-    relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices,
+    relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices, comm=comm,
                                  ops_factory=None if use_native else NumpyOps)
+    assert relax.use_p2p == (comm == "p2p")
     if use_native:
       xn = torch.from_numpy(xn0[r0:r1].copy()).cuda()
       xe = torch.from_numpy(xe0.copy()).cuda()

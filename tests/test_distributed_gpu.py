@@ -35,19 +35,38 @@ def _check(tmp_path, world, graph_args, R, iters):
   assert np.abs(got_xn - ref_xn).max() < 2e-5
 
 
-@pytest.mark.parametrize("slices", [1, 4])
-def test_one_rank_nccl(tmp_path, slices):
+@pytest.mark.parametrize("slices,comm", [(1, "nccl"), (4, "nccl"), (1, "p2p")])
+def test_one_rank(tmp_path, slices, comm):
   graph_args = (9, 20000, 700, 150000)
   mp.spawn(dist_helpers.worker,
-           args=(1, _free_port(), "nccl", graph_args, 32, 8, slices, str(tmp_path), True),
+           args=(1, _free_port(), "nccl", graph_args, 32, 8, slices, str(tmp_path), True, comm),
            nprocs=1, join=True)
   _check(tmp_path, 1, graph_args, 32, 8)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_ranks_nccl(tmp_path):
+@pytest.mark.parametrize("comm,R", [("nccl", 32), ("p2p", 32), ("p2p", 10)])
+def test_two_ranks(tmp_path, comm, R):
+  """2 ranks on 2 GPUs; the peer-memory exchange and the NCCL exchange give the oracle's result."""
   graph_args = (10, 30000, 900, 250000)
   mp.spawn(dist_helpers.worker,
-           args=(2, _free_port(), "nccl", graph_args, 32, 8, 4, str(tmp_path), True),
+           args=(2, _free_port(), "nccl", graph_args, R, 8, 4 if comm == "nccl" else 1,
+                 str(tmp_path), True, comm),
            nprocs=2, join=True)
-  _check(tmp_path, 2, graph_args, 32, 8)
+  _check(tmp_path, 2, graph_args, R, 8)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_ranks_p2p_is_reproducible(tmp_path):
+  graph_args = (11, 20000, 500, 200000)
+  outs = []
+  for rep in range(2):
+    d = tmp_path / ("rep%d" % rep)
+    d.mkdir()
+    mp.spawn(dist_helpers.worker,
+             args=(2, _free_port(), "nccl", graph_args, 32, 6, 1, str(d), True, "p2p"),
+             nprocs=2, join=True)
+    outs.append([np.load(d / ("rank%d.npz" % r)) for r in range(2)])
+  for r in range(2):
+    assert np.array_equal(outs[0][r]["xn"], outs[1][r]["xn"])
+    assert np.array_equal(outs[0][r]["xe"], outs[1][r]["xe"])
