@@ -41,21 +41,37 @@ __global__ void k_row_degree(int32_t rows, const int64_t* __restrict__ ptr,
     deg[r] = (int32_t)(ptr[r + 1] - ptr[r]);
 }
 
-// wsum[r] = sum_{b in row r} 1 / other_deg[b], accumulated in f64 (one warp per row).
+// wsum[r] = sum_{b in row r} 1 / other_deg[b], accumulated in f64 (8 lanes per row).
 __global__ void k_row_wsum(int32_t rows, const int64_t* __restrict__ ptr,
                            const int32_t* __restrict__ idx,
                            const int32_t* __restrict__ other_deg, double* __restrict__ wsum) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
-       r += nw) {
-    const int64_t b = ptr[r], e = ptr[r + 1];
+  const int sub = threadIdx.x & 7;
+  const int64_t ng = (int64_t)gridDim.x * (blockDim.x >> 3);
+  const int64_t g0 = blockIdx.x * (int64_t)(blockDim.x >> 3) + (threadIdx.x >> 3);
+  // every lane of a warp runs the same number of outer iterations (full-mask shuffles below)
+  for (int64_t base = 0; base < rows; base += ng) {
+    const int64_t r = base + g0;
     double s = 0.0;
-    for (int64_t p = b + lane; p < e; p += 32) s += 1.0 / (double)other_deg[idx[p]];
+    if (r < rows) {
+      const int64_t b = ptr[r], e = ptr[r + 1];
+      for (int64_t p = b + sub; p < e; p += 8) s += 1.0 / (double)other_deg[idx[p]];
+    }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-    if (lane == 0) wsum[r] = s;
+    for (int off = 4; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    if (r < rows && sub == 0) wsum[r] = s;
   }
+}
+
+// The work items are built on the host before the inverse weight sums exist on the device;
+// these two kernels fill them in, so that incidence creation never waits for the GPU.
+__global__ void k_patch_light(int64_t n, HgeLightItem* items, const float* __restrict__ invs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (items[i].row >= 0) items[i].invs = invs[items[i].row];
+}
+__global__ void k_patch_heavy(int32_t n, HgeHeavyRow* rows, const float* __restrict__ invs) {
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    rows[i].invs = invs[rows[i].row];
 }
 
 __global__ void k_invert(int32_t rows, const double* __restrict__ wsum, float* __restrict__ invs) {
@@ -518,40 +534,36 @@ int grid_1d(const hge_ctx* ctx, int64_t work, int block) {
 int compute_wsum(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, const int32_t* d_idx,
                  const int32_t* d_other_deg, double** wsum) {
   HGE_TRY(hge_dev_alloc(ctx, wsum, (size_t)rows));
-  k_row_wsum<<<grid_1d(ctx, (int64_t)rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
+  k_row_wsum<<<grid_1d(ctx, (int64_t)rows * 8, kBlock), kBlock, 0, ctx->stream>>>(
       rows, d_ptr, d_idx, d_other_deg, *wsum);
   HGE_CHECK_LAUNCH(ctx);
   return HGE_OK;
 }
 
-// invs = 1 / wsum as fp32, on the device and mirrored on the host for the work items.
-int invert_wsum(hge_ctx* ctx, int32_t rows, const double* wsum, float** invs,
-                std::vector<float>* h_invs) {
+// invs = 1 / wsum as fp32 (device).
+int invert_wsum(hge_ctx* ctx, int32_t rows, const double* wsum, float** invs) {
   HGE_TRY(hge_dev_alloc(ctx, invs, (size_t)rows));
   k_invert<<<grid_1d(ctx, rows, kBlock), kBlock, 0, ctx->stream>>>(rows, wsum, *invs);
   HGE_CHECK_LAUNCH(ctx);
-  h_invs->resize((size_t)rows);
-  HGE_CUDA(cudaMemcpyAsync(h_invs->data(), *invs, (size_t)rows * sizeof(float),
-                           cudaMemcpyDeviceToHost, ctx->stream));
-  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
   return HGE_OK;
 }
 
 // Work items for rows [row0, row1) of one CSR.  ptr / idx / deg / invs of `s` are set by the
-// caller (slices of the sharded edge half share them).
+// caller (slices of the sharded edge half share them).  The items are written straight into
+// pinned memory, copied asynchronously and completed on the device (k_patch_*): no host wait.
 int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
-                        const std::vector<int64_t>& h_ptr, const std::vector<float>& h_invs,
-                        const char* what, HgeHalfSchedule* s) {
+                        const std::vector<int64_t>& h_ptr, const char* what, HgeHalfSchedule* s) {
   s->rows = row1 - row0;
   s->nnz = h_ptr[row1] - h_ptr[row0];
   s->chunk_sz = ctx->chunk;
   const int light_max = ctx->light_max_deg;
   const int chunk = ctx->chunk;
 
-  // counting sort of the light rows by descending degree; long rows sorted by degree too
+  // pass 1: degree histogram of the short rows, list of the long rows
   std::vector<int64_t> bucket((size_t)light_max + 2, 0);
   std::vector<std::pair<int32_t, int32_t>> heavy;  // (deg, row)
   int32_t max_deg = 0;
+  int64_t n_chunks = 0;
   for (int32_t r = row0; r < row1; ++r) {
     const int64_t d = h_ptr[r + 1] - h_ptr[r];
     if (d <= 0) {
@@ -566,19 +578,39 @@ int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
       return HGE_ERR_UNSUPPORTED;
     }
     max_deg = std::max<int32_t>(max_deg, (int32_t)d);
-    if (d <= light_max) bucket[(size_t)d]++;
-    else heavy.emplace_back((int32_t)d, r);
+    if (d <= light_max) {
+      bucket[(size_t)d]++;
+    } else {
+      heavy.emplace_back((int32_t)d, r);
+      n_chunks += (d + chunk - 1) / chunk;
+    }
   }
   s->max_deg = max_deg;
-  // offsets: degree light_max first ... degree 0 last
-  std::vector<int64_t> offset((size_t)light_max + 2, 0);
-  int64_t run = 0;
-  for (int d = light_max; d >= 0; --d) {
-    offset[(size_t)d] = run;
-    run += bucket[(size_t)d];
+  if (n_chunks > INT32_MAX) {
+    hge_set_error("%s schedule needs more than 2^31-1 chunks", what);
+    return HGE_ERR_UNSUPPORTED;
   }
-  s->n_light = run;
-  std::vector<HgeLightItem> light((size_t)run);
+  // offsets: degree light_max first ... degree 0 last (longest work first)
+  std::vector<int64_t> offset((size_t)light_max + 2, 0);
+  int64_t n_light = 0;
+  for (int d = light_max; d >= 0; --d) {
+    offset[(size_t)d] = n_light;
+    n_light += bucket[(size_t)d];
+  }
+  s->n_light = n_light;
+  s->n_hrows = (int32_t)heavy.size();
+  s->n_chunks = (int32_t)n_chunks;
+
+  const size_t light_bytes = (size_t)n_light * sizeof(HgeLightItem);
+  const size_t hrow_bytes = heavy.size() * sizeof(HgeHeavyRow);
+  const size_t chunk_bytes = (size_t)n_chunks * sizeof(int2);
+  char* pinned = static_cast<char*>(hge_ctx_pinned(ctx, light_bytes + hrow_bytes + chunk_bytes + 64));
+  if (!pinned) return HGE_ERR_NOMEM;
+  HgeLightItem* light = reinterpret_cast<HgeLightItem*>(pinned);
+  HgeHeavyRow* hrows = reinterpret_cast<HgeHeavyRow*>(pinned + light_bytes);
+  int2* chunks = reinterpret_cast<int2*>(pinned + light_bytes + hrow_bytes);
+
+  // pass 2: counting sort of the short rows by descending degree
   for (int32_t r = row0; r < row1; ++r) {
     const int64_t d = h_ptr[r + 1] - h_ptr[r];
     if (d > light_max) continue;
@@ -586,16 +618,15 @@ int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
     it.row = r;
     it.deg_hi = (uint32_t)d | (uint32_t)((h_ptr[r] >> 32) << 8);
     it.start_lo = (uint32_t)(h_ptr[r] & 0xffffffffll);
-    it.invs = h_invs[(size_t)r];
-    light[(size_t)offset[(size_t)d]++] = it;
+    it.invs = 0.f;
+    light[offset[(size_t)d]++] = it;
   }
   std::sort(heavy.begin(), heavy.end(), [](const std::pair<int32_t, int32_t>& x,
                                            const std::pair<int32_t, int32_t>& y) {
     return x.first != y.first ? x.first > y.first : x.second < y.second;
   });
-  std::vector<HgeHeavyRow> hrows(heavy.size());
-  std::vector<int2> chunks;
   int32_t n_partials = 0;
+  int64_t c = 0;
   for (size_t h = 0; h < heavy.size(); ++h) {
     HgeHeavyRow& hr = hrows[h];
     hr.row = heavy[h].second;
@@ -607,30 +638,31 @@ int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
       hr.partial_base = n_partials;
       n_partials += hr.nchunks;
     }
-    hr.invs = h_invs[(size_t)hr.row];
+    hr.invs = 0.f;
     hr.pad = 0;
+    // the chunks of the longest rows first, so their reductions finish early
+    for (int32_t k = 0; k < hr.nchunks; ++k) chunks[c++] = make_int2((int)h, k);
   }
-  // chunk order: round-robin over rows sorted by size would serialise nothing; simply emit
-  // the chunks of the longest rows first so their reductions finish early.
-  for (size_t h = 0; h < heavy.size(); ++h)
-    for (int32_t c = 0; c < hrows[h].nchunks; ++c) chunks.push_back(make_int2((int)h, c));
-  s->n_hrows = (int32_t)hrows.size();
-  s->n_chunks = (int32_t)chunks.size();
   s->n_partials = n_partials;
 
-  HGE_TRY(hge_dev_alloc(ctx, &s->light, light.size()));
-  HGE_TRY(hge_dev_alloc(ctx, &s->hrows, hrows.size()));
-  HGE_TRY(hge_dev_alloc(ctx, &s->chunks, chunks.size()));
-  if (!light.empty())
-    HGE_CUDA(cudaMemcpyAsync(s->light, light.data(), light.size() * sizeof(HgeLightItem),
-                             cudaMemcpyHostToDevice, ctx->stream));
-  if (!hrows.empty())
-    HGE_CUDA(cudaMemcpyAsync(s->hrows, hrows.data(), hrows.size() * sizeof(HgeHeavyRow),
-                             cudaMemcpyHostToDevice, ctx->stream));
-  if (!chunks.empty())
-    HGE_CUDA(cudaMemcpyAsync(s->chunks, chunks.data(), chunks.size() * sizeof(int2),
-                             cudaMemcpyHostToDevice, ctx->stream));
-  HGE_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  HGE_TRY(hge_dev_alloc(ctx, &s->light, (size_t)n_light));
+  HGE_TRY(hge_dev_alloc(ctx, &s->hrows, heavy.size()));
+  HGE_TRY(hge_dev_alloc(ctx, &s->chunks, (size_t)n_chunks));
+  if (light_bytes)
+    HGE_CUDA(cudaMemcpyAsync(s->light, light, light_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (hrow_bytes)
+    HGE_CUDA(cudaMemcpyAsync(s->hrows, hrows, hrow_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (chunk_bytes)
+    HGE_CUDA(cudaMemcpyAsync(s->chunks, chunks, chunk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_light) {
+    k_patch_light<<<grid_1d(ctx, n_light, kBlock), kBlock, 0, ctx->stream>>>(n_light, s->light, s->invs);
+    HGE_CHECK_LAUNCH(ctx);
+  }
+  if (!heavy.empty()) {
+    k_patch_heavy<<<grid_1d(ctx, (int64_t)heavy.size(), kBlock), kBlock, 0, ctx->stream>>>(
+        (int32_t)heavy.size(), s->hrows, s->invs);
+    HGE_CHECK_LAUNCH(ctx);
+  }
   return HGE_OK;
 }
 
@@ -731,6 +763,7 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
 
   hge_incidence* inc = new (std::nothrow) hge_incidence();
   if (!inc) return HGE_ERR_NOMEM;
+  hge_ctx_pinned_reset(ctx);
   inc->ctx = ctx;
   inc->N = num_nodes;
   inc->E = num_edges;
@@ -825,15 +858,14 @@ static int incidence_finish(hge_incidence* inc) {
   hge_ctx* ctx = inc->ctx;
   HgeHalfSchedule& nh = inc->node_half;
   HgeHalfSchedule& eh = inc->edge_half;
-  std::vector<float> h_invs_n, h_invs_e;
   double* node_wsum = nullptr;
   HGE_TRY(compute_wsum(ctx, inc->N, inc->n2e_ptr, inc->n2e_idx, eh.deg, &node_wsum));
-  int rc = invert_wsum(ctx, inc->N, node_wsum, &nh.invs, &h_invs_n);
+  int rc = invert_wsum(ctx, inc->N, node_wsum, &nh.invs);
   hge_dev_free(ctx, node_wsum);
   if (rc != HGE_OK) return rc;
-  HGE_TRY(invert_wsum(ctx, inc->E, inc->edge_wsum, &eh.invs, &h_invs_e));
-  HGE_TRY(build_half_schedule(ctx, 0, inc->N, inc->h_n2e_ptr, h_invs_n, "node", &nh));
-  HGE_TRY(build_half_schedule(ctx, 0, inc->E, inc->h_e2n_ptr, h_invs_e, "edge", &eh));
+  HGE_TRY(invert_wsum(ctx, inc->E, inc->edge_wsum, &eh.invs));
+  HGE_TRY(build_half_schedule(ctx, 0, inc->N, inc->h_n2e_ptr, "node", &nh));
+  HGE_TRY(build_half_schedule(ctx, 0, inc->E, inc->h_e2n_ptr, "edge", &eh));
   if (inc->sharded) {
     // the sharded edge half runs slice by slice so that the all-reduce of one slice's partial
     // sums overlaps the gather of the next
@@ -849,7 +881,7 @@ static int incidence_finish(hge_incidence* inc) {
       sl.deg = eh.deg;
       sl.invs = eh.invs;
       HGE_TRY(build_half_schedule(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
-                                  inc->h_e2n_ptr, h_invs_e, "edge", &sl));
+                                  inc->h_e2n_ptr, "edge", &sl));
     }
   }
   inc->finished = true;

@@ -51,7 +51,19 @@ struct hge_ctx {
   int chunk;
   int blocks_per_sm;
   int64_t launches;
+  // pinned staging arena (bump allocation; chunks are kept for re-use)
+  void* pinned_chunk[32];
+  size_t pinned_size[32];
+  int pinned_chunks;
+  int pinned_cur;
+  size_t pinned_off;
+  bool pinned_in_flight;
 };
+
+// Pinned host memory that stays valid until the next hge_ctx_pinned_reset (which drains the
+// stream first if copies out of the arena may still be running).  nullptr on failure.
+void* hge_ctx_pinned(hge_ctx* ctx, size_t bytes);
+void hge_ctx_pinned_reset(hge_ctx* ctx);
 
 // Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the
 // context's stream; hge_ctx_create raises the pool's release threshold so freed blocks are

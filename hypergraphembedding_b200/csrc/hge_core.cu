@@ -15,6 +15,44 @@ void hge_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+void* hge_ctx_pinned(hge_ctx* ctx, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  ctx->pinned_in_flight = true;
+  // first chunk at or after the current one with room
+  for (int k = ctx->pinned_cur; k < ctx->pinned_chunks; ++k) {
+    const size_t off = (k == ctx->pinned_cur) ? ctx->pinned_off : 0;
+    if (off + bytes <= ctx->pinned_size[k]) {
+      ctx->pinned_cur = k;
+      ctx->pinned_off = off + bytes;
+      return static_cast<char*>(ctx->pinned_chunk[k]) + off;
+    }
+  }
+  if (ctx->pinned_chunks == 32) {
+    hge_set_error("pinned staging arena exhausted");
+    return nullptr;
+  }
+  const size_t size = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+  void* p = nullptr;
+  if (cudaMallocHost(&p, size) != cudaSuccess) {
+    cudaGetLastError();
+    hge_set_error("cudaMallocHost of %zu bytes failed", size);
+    return nullptr;
+  }
+  const int k = ctx->pinned_chunks++;
+  ctx->pinned_chunk[k] = p;
+  ctx->pinned_size[k] = size;
+  ctx->pinned_cur = k;
+  ctx->pinned_off = bytes;
+  return p;
+}
+
+void hge_ctx_pinned_reset(hge_ctx* ctx) {
+  if (ctx->pinned_in_flight) cudaStreamSynchronize(ctx->stream);
+  ctx->pinned_in_flight = false;
+  ctx->pinned_cur = 0;
+  ctx->pinned_off = 0;
+}
+
 extern "C" {
 
 int hge_version(void) { return 100; }
@@ -50,6 +88,10 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->chunk = 512;
   ctx->blocks_per_sm = 0;  // 0: ask the occupancy calculator
   ctx->launches = 0;
+  ctx->pinned_chunks = 0;
+  ctx->pinned_cur = 0;
+  ctx->pinned_off = 0;
+  ctx->pinned_in_flight = false;
   // NULL selects the legacy default stream, which is also torch's default stream, so work
   // queued by the caller on that stream is ordered with ours.
   ctx->stream = reinterpret_cast<cudaStream_t>(stream);
@@ -67,6 +109,8 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
 int hge_ctx_destroy(hge_ctx* ctx) {
   if (!ctx) return HGE_OK;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < ctx->pinned_chunks; ++k) cudaFreeHost(ctx->pinned_chunk[k]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HGE_OK;
