@@ -40,6 +40,12 @@ WORKLOADS = {
     "c2": dict(kind="power_law", num_nodes=1000000, num_edges=500000, num_incidences=10000000,
                R=32, sweeps=20, seed=1234,
                name="synthetic power-law hypergraph 1M nodes / 500K edges / 10M incidences, R=32, 20 sweeps"),
+    # BASELINE.json configs[4]: strong scaling, generated on the device shard by shard
+    "c5": dict(kind="community", num_nodes=65000000, num_edges=1000000, num_incidences=1800000000,
+               R=32, sweeps=20, seed=99,
+               name="Friendster-community-shaped synthetic hypergraph 65M nodes / 1M edges / 1.8B incidences, R=32, 20 sweeps"),
+    "c5mini": dict(kind="community", num_nodes=650000, num_edges=10000, num_incidences=18000000,
+                   R=32, sweeps=20, seed=99, name="1/100-scale config 5 (debug)"),
     # small variant for quick checks (not a bench line)
     "mini": dict(kind="power_law", num_nodes=100000, num_edges=50000, num_incidences=1000000,
                  R=32, sweeps=20, seed=1234, name="1/10-scale config 2 (debug)"),
@@ -91,6 +97,25 @@ def hbm_peak():
     except Exception:
       pass
   return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def init_process_group_quiet(rank, world, device):
+  """torch.distributed over NCCL with stdout pointed at stderr while the communicator comes
+  up: NCCL prints its version banner on stdout, and rank 0 must print exactly one JSON line."""
+  import torch
+  import torch.distributed as dist
+  sys.stdout.flush()
+  saved = os.dup(1)
+  os.dup2(2, 1)
+  try:
+    dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=device)
+    probe = torch.zeros(1, device=device)
+    dist.all_reduce(probe)
+    torch.cuda.synchronize()
+  finally:
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
 
 
 class ClockSampler(object):
@@ -289,6 +314,8 @@ def run_ours(args, spec):
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if spec["kind"] == "community":
+    return run_community(args, spec, world, rank, local_rank)
   if world > 1:
     return run_sharded(args, spec, world, rank, local_rank)
   torch.cuda.set_device(local_rank)
@@ -434,6 +461,157 @@ def run_ours(args, spec):
   print(json.dumps(out), flush=True)
 
 
+def community_shard_device(spec, rank, world, device):
+  """One node block of the config-5 family, generated on the GPU (the host generators would
+  need minutes and > 100 GB for 1.8B incidences).  Global shape: edge sizes ~ power law
+  (exponent 1.5) on [3, 1e6] scaled to the incidence budget, members uniform; every node
+  additionally joins one uniformly random edge, so no node is isolated.  Rank r holds nodes
+  [r N / P, (r+1) N / P) and of every edge the share  size // P (+1 for the first size % P
+  ranks)  of its members, drawn uniformly from the block.  Returns device CSR tensors of the
+  block in both orientations (sorted, unique column ids)."""
+  import torch
+  N, E, nnz = spec["num_nodes"], spec["num_edges"], spec["num_incidences"]
+  n0, n1 = N * rank // world, N * (rank + 1) // world
+  n_loc = n1 - n0
+  rng = np.random.Generator(np.random.PCG64(spec["seed"]))          # same sizes on every rank
+  u = rng.random(E)
+  a, lo, hi = 1.0 - 1.5, 3.0, 1.0e6
+  raw = ((hi**a - lo**a) * u + lo**a)**(1.0 / a)
+  sizes = np.clip(raw * ((nnz - N) / raw.sum()), lo, min(hi, N // 2)).astype(np.int64)
+  local = sizes // world + (rank < (sizes % world)).astype(np.int64)
+  gen = torch.Generator(device=device)
+  gen.manual_seed(spec["seed"] * 1000 + rank)
+  sizes_t = torch.from_numpy(local).to(device)
+  edge_of = torch.repeat_interleave(torch.arange(E, device=device, dtype=torch.int64), sizes_t)
+  node_of = torch.randint(0, n_loc, (edge_of.numel(),), device=device, generator=gen)
+  keys = edge_of * n_loc + node_of
+  del edge_of, node_of
+  extra_e = torch.randint(0, E, (n_loc,), device=device, generator=gen)
+  keys = torch.cat([keys, extra_e * n_loc + torch.arange(n_loc, device=device, dtype=torch.int64)])
+  del extra_e
+  keys = torch.unique(keys)                                          # sorted, duplicates removed
+  e_idx = torch.div(keys, n_loc, rounding_mode="floor")
+  n_idx = keys - e_idx * n_loc
+  del keys
+  b_idx = n_idx.to(torch.int32)
+  b_ptr = torch.zeros(E + 1, dtype=torch.int64, device=device)
+  b_ptr[1:] = torch.cumsum(torch.bincount(e_idx, minlength=E), 0)
+  keys2 = n_idx * E + e_idx
+  del n_idx, e_idx
+  keys2, _ = torch.sort(keys2)
+  n_row = torch.div(keys2, E, rounding_mode="floor")
+  a_idx = (keys2 - n_row * E).to(torch.int32)
+  del keys2
+  a_ptr = torch.zeros(n_loc + 1, dtype=torch.int64, device=device)
+  a_ptr[1:] = torch.cumsum(torch.bincount(n_row, minlength=n_loc), 0)
+  del n_row
+  torch.cuda.empty_cache()
+  return dict(n_loc=n_loc, E=E, a_ptr=a_ptr, a_idx=a_idx, b_ptr=b_ptr, b_idx=b_idx,
+              nnz=int(a_idx.numel()))
+
+
+def run_community(args, spec, world, rank, local_rank):
+  """--workload c5 / c5mini: strong scaling of one fixed hypergraph over the ranks (N = 1: the
+  plain single-GPU path).  Device-resident arm only."""
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import _native
+  from hypergraphembedding_b200 import distributed as hd
+
+  torch.cuda.set_device(local_rank)
+  device = torch.device("cuda", local_rank)
+  if world > 1:
+    init_process_group_quiet(rank, world, device)
+  ctx = _native.default_context(local_rank)
+  t = time.time()
+  g = community_shard_device(spec, rank, world, device)
+  torch.cuda.synchronize()
+  gen_s = time.time() - t
+  n_loc, E, R, sweeps = g["n_loc"], g["E"], spec["R"], spec["sweeps"]
+  nnz_t = torch.tensor([g["nnz"]], dtype=torch.int64, device=device)
+  if world > 1:
+    dist.all_reduce(nnz_t)
+  nnz_global = int(nnz_t.item())
+  gen = torch.Generator(device=device)
+  gen.manual_seed(7 + rank)
+  xn_init = torch.rand((n_loc, R), device=device, generator=gen)
+  gen.manual_seed(10**6)
+  xe_init = torch.rand((E, R), device=device, generator=gen)       # identical on every rank
+  xn, xe = torch.empty_like(xn_init), torch.empty_like(xe_init)
+
+  if world == 1:
+    inc = _native.Incidence(ctx, n_loc, E, g["a_ptr"], g["a_idx"], g["b_ptr"], g["b_idx"])
+    relax, comm = None, "single GPU"
+
+    def step():
+      xn.copy_(xn_init)
+      xe.copy_(xe_init)
+      _native.algdist_run(ctx, inc, xn, xe, sweeps)
+  else:
+    relax = hd.ShardedRelaxation(None, R, sweeps, comm=args.comm, num_slices=args.slices, ctx=ctx,
+                                 shape=(n_loc, E),
+                                 csr_device=(g["a_ptr"], g["a_idx"], g["b_ptr"], g["b_idx"]))
+    comm = "p2p" if relax.use_p2p else "nccl"
+
+    def step():
+      xn.copy_(xn_init)
+      xe.copy_(xe_init)
+      relax.run(xn, xe)
+
+  for _ in range(args.warmup):
+    step()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = ctx.launch_count
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  ev0.record()
+  for _ in range(args.steps):
+    step()
+  ev1.record()
+  torch.cuda.synchronize()
+  ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+  if world > 1:
+    dist.barrier()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  ms_per_step = float(ms.item()) / args.steps
+  launches = ctx.launch_count - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  value = nnz_global * R * sweeps / (ms_per_step * 1e-3)
+  N = spec["num_nodes"]
+  bytes_step = algorithmic_bytes_per_sweep(N, E, nnz_global, R) * sweeps
+  achieved = bytes_step / (ms_per_step * 1e-3) / 1e9 / world      # per GPU, whole step
+  peak, peak_src = hbm_peak()
+  finite = bool(torch.isfinite(xn).all().item() and torch.isfinite(xe).all().item())
+  span_ok = bool((xe.min() >= -1e-6).item() and (xe.max() <= 1 + 1e-6).item())
+  if relax is not None:
+    relax.close()
+  if rank == 0:
+    out = {
+        "metric": "alg-dist incidence nnz*R*iters/sec", "value": value, "unit": "nnz*R*iters/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": spec["name"], "nodes": N, "edges": E, "nnz": nnz_global,
+                   "nnz_per_gpu": g["nnz"], "R": R, "sweeps": sweeps, "seed": spec["seed"],
+                   "exchange": comm, "generate_s": gen_s, "result_finite": finite,
+                   "result_in_unit_cube": span_ok,
+                   "l2": "no flush: per-GPU working set exceeds the 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": "whole step (load + %d sweeps + store), per GPU" % sweeps,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_step / world, "ms_per_launch": ms_per_step},
+        "cpu_baseline": None, "e2e": None,
+        "gpu_launches": int(launches) * world, "clocks": clocks,
+    }
+    print(json.dumps(out), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def run_sharded(args, spec, world, rank, local_rank):
   """N > 1: weak scaling.  Every rank owns one config-2-shaped block of node rows (its own
   seed) over the same 500K edges; the global hypergraph is the stack of the blocks."""
@@ -443,10 +621,7 @@ def run_sharded(args, spec, world, rank, local_rank):
   from hypergraphembedding_b200 import distributed as hd
 
   torch.cuda.set_device(local_rank)
-  if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout (one JSON line)
-  dist.init_process_group(backend="nccl", rank=rank, world_size=world,
-                          device_id=torch.device("cuda", local_rank))
+  init_process_group_quiet(rank, world, torch.device("cuda", local_rank))
   ctx = _native.default_context(local_rank)
   if os.environ.get("HGE_BLOCKS_PER_SM"):
     ctx.set_tuning(0, 0, int(os.environ["HGE_BLOCKS_PER_SM"]))

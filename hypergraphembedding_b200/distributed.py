@@ -53,24 +53,33 @@ class _CudaView(object):
 class NativeOps(object):
   """The per-rank kernels of libhge_b200.so behind the interface ShardedRelaxation drives."""
 
-  def __init__(self, A_local, R, iterations, num_slices, ctx=None, B_local=None):
+  def __init__(self, A_local, R, iterations, num_slices, ctx=None, B_local=None, shape=None,
+               csr_device=None):
+    """A_local: scipy n_local x E incidence block (B_local: its transpose, optional), or
+    csr_device = (n2e_ptr, n2e_idx, e2n_ptr, e2n_idx) torch CUDA tensors with shape=(n_local, E)."""
     import torch
     self.torch = torch
     self.ctx = ctx or _native.default_context()
     self.device = torch.device("cuda", self.ctx.device)
-    A = sps.csr_matrix(A_local)
-    if B_local is None:
-      B = A.T.tocsr()
-      B.sort_indices()
-    else:
-      B = B_local
     self.R, self.iterations = R, iterations
-    self.inc = _native.Incidence(self.ctx, A.shape[0], A.shape[1],
-                                 np.asarray(A.indptr, np.int64), np.asarray(A.indices, np.int32),
-                                 np.asarray(B.indptr, np.int64), np.asarray(B.indices, np.int32),
-                                 sharded=True, num_slices=num_slices)
+    if csr_device is not None:
+      n_loc, num_edges = shape
+      self.inc = _native.Incidence(self.ctx, n_loc, num_edges, *csr_device, sharded=True,
+                                   num_slices=num_slices)
+    else:
+      A = sps.csr_matrix(A_local)
+      if B_local is None:
+        B = A.T.tocsr()
+        B.sort_indices()
+      else:
+        B = B_local
+      n_loc, num_edges = A.shape
+      self.inc = _native.Incidence(self.ctx, n_loc, num_edges,
+                                   np.asarray(A.indptr, np.int64), np.asarray(A.indices, np.int32),
+                                   np.asarray(B.indptr, np.int64), np.asarray(B.indices, np.int32),
+                                   sharded=True, num_slices=num_slices)
     self.num_slices = num_slices
-    self.num_edges = A.shape[1]
+    self.num_edges = num_edges
     self.state = None
 
   def edge_sums(self):
@@ -156,7 +165,7 @@ class ShardedRelaxation(object):
     self.torch, self.dist, self.group = torch, dist, group
     self.R, self.iterations = int(R), int(iterations)
     self.check_barriers = True
-    self.num_local_nodes, self.num_edges = A_local.shape
+    self.num_local_nodes, self.num_edges = ops_kwargs.get("shape") or A_local.shape
     num_slices = max(1, min(int(num_slices), self.num_edges))
     factory = ops_factory or NativeOps
     self.ops = factory(A_local, self.R, self.iterations, num_slices, **ops_kwargs)
