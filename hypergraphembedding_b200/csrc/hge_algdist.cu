@@ -146,6 +146,7 @@ struct HalfSweepArgs {
   float4* const* push_stage;
   int32_t push_rows;
   int32_t push_rank;
+  int32_t skip_heavy;          // 1: the long rows are gathered by k_heavy_bulk instead
   int32_t R;
   int32_t ld4;
 };
@@ -222,55 +223,63 @@ __device__ __forceinline__ void accumulate(float4& s, float4& c, float4 (&v)[N])
 #endif
 }
 
-template <int LPR>
 #ifndef HGE_MIN_BLOCKS
 #define HGE_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const HalfSweepArgs a) {
-  constexpr int G = 32 / LPR;                       // rows per warp on the light path
-  constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
-  constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
 
-  const int lane = threadIdx.x & 31;
-  const int gl = lane & (LPR - 1);
-  const int g = lane / LPR;
-  const int warp = threadIdx.x >> 5;
-  const int slab = blockIdx.y;                      // column slab of 32 float4 (R > 128 only)
-  const int c4 = slab * LPR + gl;                   // this lane's float4 column
-  const bool active = c4 < a.ld4;
-  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
-  const int64_t nw = (int64_t)gridDim.x * kWarps;
-  const int ld4 = a.ld4;
-  const int col0 = c4 * 4;
-  const bool m0 = col0 + 0 < a.R, m1 = col0 + 1 < a.R, m2 = col0 + 2 < a.R, m3 = col0 + 3 < a.R;
-
+// Per-thread state shared by the two gather kernels: which float4 column of which sub-warp this
+// lane is, the lazily applied affine map of the previous sweep, the running per-column min /
+// max, and what to do with a finished row.
+template <int LPR>
+struct RowOwner {
+  static constexpr int G = 32 / LPR;
+  const HalfSweepArgs& a;
+  int lane, gl, g, warp, slab, c4, ld4;
+  bool active, gaff, raw_out, m0, m1, m2, m3;
   Affine af;
-  af.inv = make_float4(1.f, 1.f, 1.f, 1.f);
-  af.invlo = hge_f4_zero();
-  if (a.mm_prev && active) {
-    float lo[4], inv[4];
+  float4 vmin, vmax;
+
+  __device__ __forceinline__ explicit RowOwner(const HalfSweepArgs& args) : a(args) {
+    lane = threadIdx.x & 31;
+    gl = lane & (LPR - 1);
+    g = lane / LPR;
+    warp = threadIdx.x >> 5;
+    slab = blockIdx.y;                      // column slab of 32 float4 (R > 128 only)
+    c4 = slab * LPR + gl;                   // this lane's float4 column
+    ld4 = a.ld4;
+    active = c4 < ld4;
+    const int col0 = c4 * 4;
+    m0 = col0 + 0 < a.R;
+    m1 = col0 + 1 < a.R;
+    m2 = col0 + 2 < a.R;
+    m3 = col0 + 3 < a.R;
+    af.inv = make_float4(1.f, 1.f, 1.f, 1.f);
+    af.invlo = hge_f4_zero();
+    if (a.mm_prev && active) {
+      float lo[4], inv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      lo[j] = 0.f;
-      inv[j] = 1.f;
-      if (col0 + j < a.R) {
-        lo[j] = hge_dec(a.mm_prev[col0 + j]);
-        const float hi = hge_dec(a.mm_prev[ld4 * 4 + col0 + j]);
-        inv[j] = 1.0f / (hi - lo[j]);
+      for (int j = 0; j < 4; ++j) {
+        lo[j] = 0.f;
+        inv[j] = 1.f;
+        if (col0 + j < a.R) {
+          lo[j] = hge_dec(a.mm_prev[col0 + j]);
+          const float hi = hge_dec(a.mm_prev[ld4 * 4 + col0 + j]);
+          inv[j] = 1.0f / (hi - lo[j]);
+        }
       }
+      af.inv = make_float4(inv[0], inv[1], inv[2], inv[3]);
+      af.invlo = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
     }
-    af.inv = make_float4(inv[0], inv[1], inv[2], inv[3]);
-    af.invlo = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
+    gaff = a.gather_affine != 0;
+    raw_out = a.raw_out != 0;
+    const float inf = __int_as_float(0x7f800000);
+    vmin = make_float4(inf, inf, inf, inf);
+    vmax = make_float4(-inf, -inf, -inf, -inf);
   }
-  const bool gaff = a.gather_affine != 0;
-  const bool raw_out = a.raw_out != 0;
 
-  const float inf = __int_as_float(0x7f800000);
-  float4 vmin = make_float4(inf, inf, inf, inf);
-  float4 vmax = make_float4(-inf, -inf, -inf, -inf);
-
-  auto finish_row = [&](int row, float degf, float invs, const float4& yown, const float4& acc) {
-    // called by the lanes that own (row, c4); acc is the full gathered sum
+  // called by the lanes that own (row, c4); acc is the full gathered sum
+  __device__ __forceinline__ void finish_row(int row, float degf, float invs, const float4& yown,
+                                             const float4& acc) {
     const size_t off = (size_t)row * ld4 + c4;
     if (raw_out) {
       if (a.raw_out == 2) {
@@ -292,13 +301,110 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
     if (m1) { vmin.y = fminf(vmin.y, x.y); vmax.y = fmaxf(vmax.y, x.y); }
     if (m2) { vmin.z = fminf(vmin.z, x.z); vmax.z = fmaxf(vmax.z, x.z); }
     if (m3) { vmin.w = fminf(vmin.w, x.w); vmax.w = fmaxf(vmax.w, x.w); }
-  };
+  }
+
+  __device__ __forceinline__ float4 load_own(int row) const {
+    return __ldcs(a.yo + (size_t)row * ld4 + c4);
+  }
+
+  __device__ __forceinline__ static void reduce_groups(float4& v) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+      v.x += __shfl_xor_sync(kFull, v.x, off);
+      v.y += __shfl_xor_sync(kFull, v.y, off);
+      v.z += __shfl_xor_sync(kFull, v.z, off);
+      v.w += __shfl_xor_sync(kFull, v.w, off);
+    }
+  }
+
+  // A warp has gathered one chunk of a long row (per-sub-warp sums in acc).  Single-chunk rows
+  // are finished here; multi-chunk rows park the chunk sum, and the last chunk of the row to
+  // arrive adds the parked sums in chunk order (deterministic) and finishes the row.
+  __device__ __forceinline__ void finish_chunk(const HgeHeavyRow& hr, const int2 ch, float4 acc,
+                                               float4 yown) {
+    reduce_groups(acc);
+    if (hr.nchunks == 1) {
+      if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, acc);
+      return;
+    }
+    if (g == 0 && active) __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
+    __threadfence();
+    __syncwarp();
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev != hr.nchunks - 1) return;
+    __threadfence();
+    if (g == 0 && active && !raw_out) yown = load_own(hr.row);
+    float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
+    for (int k = g; k < hr.nchunks; k += G)
+      if (active)
+        kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+    tot = kahan_result(tot, tcomp);
+    reduce_groups(tot);
+    if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, tot);
+    if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
+  }
+
+  // Per-column min / max of the rows this block produced: warp shuffles, shared memory, one
+  // atomic per column per block.
+  template <int WARPS>
+  __device__ __forceinline__ void publish_minmax(float4 (*smin)[LPR], float4 (*smax)[LPR]) {
+    if (raw_out) return;    // uniform over the grid
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+      vmin.x = fminf(vmin.x, __shfl_xor_sync(kFull, vmin.x, off));
+      vmin.y = fminf(vmin.y, __shfl_xor_sync(kFull, vmin.y, off));
+      vmin.z = fminf(vmin.z, __shfl_xor_sync(kFull, vmin.z, off));
+      vmin.w = fminf(vmin.w, __shfl_xor_sync(kFull, vmin.w, off));
+      vmax.x = fmaxf(vmax.x, __shfl_xor_sync(kFull, vmax.x, off));
+      vmax.y = fmaxf(vmax.y, __shfl_xor_sync(kFull, vmax.y, off));
+      vmax.z = fmaxf(vmax.z, __shfl_xor_sync(kFull, vmax.z, off));
+      vmax.w = fmaxf(vmax.w, __shfl_xor_sync(kFull, vmax.w, off));
+    }
+    if (g == 0) {
+      smin[warp][gl] = vmin;
+      smax[warp][gl] = vmax;
+    }
+    __syncthreads();
+    if (threadIdx.x < LPR * 4) {
+      const int l = threadIdx.x >> 2, j = threadIdx.x & 3;
+      const int col = (slab * LPR + l) * 4 + j;
+      if (col < a.R) {
+        const float inf = __int_as_float(0x7f800000);
+        float lo = inf, hi = -inf;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+          lo = fminf(lo, reinterpret_cast<const float*>(&smin[w][l])[j]);
+          hi = fmaxf(hi, reinterpret_cast<const float*>(&smax[w][l])[j]);
+        }
+        if (lo <= hi) {  // this block produced at least one row
+          atomicMin(a.mm_cur + col, hge_enc(lo));
+          atomicMax(a.mm_cur + ld4 * 4 + col, hge_enc(hi));
+        }
+      }
+    }
+  }
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const HalfSweepArgs a) {
+  constexpr int G = 32 / LPR;                       // rows per warp on the light path
+  constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
+  constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
+
+  RowOwner<LPR> own(a);
+  const int lane = own.lane, gl = own.gl, g = own.g, c4 = own.c4, ld4 = own.ld4;
+  const bool active = own.active, raw_out = own.raw_out;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + own.warp;
+  const int64_t nw = (int64_t)gridDim.x * kWarps;
 
   // ---- long rows: one warp per chunk of the row --------------------------------------
   // Loads are software-pipelined: the descriptor of the next chunk and the next block of 32
   // column ids are requested before the current block's rows are consumed, so a warp pays
-  // one memory latency per block of 32 gathered rows.
-  {
+  // one memory latency per block of 32 gathered rows.  (Skipped when the bulk-copy kernel
+  // below has taken the long rows.)
+  if (!a.skip_heavy) {
     int2 ch_next = make_int2(0, 0);
     if (gw < a.n_chunks) ch_next = __ldcs(a.chunks + gw);
     for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
@@ -308,9 +414,8 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
       const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
       const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
       const int32_t* cidx = a.idx + start;
-      const bool single = hr.nchunks == 1;
       float4 yown = hge_f4_zero();
-      if (single && g == 0 && active && !raw_out) yown = __ldcs(a.yo + (size_t)hr.row * ld4 + c4);
+      if (hr.nchunks == 1 && g == 0 && active && !raw_out) yown = own.load_own(hr.row);
       float4 acc = hge_f4_zero(), comp = hge_f4_zero();
       int my = (lane < count) ? __ldcs(cidx + lane) : -1;
       for (int base = 0; base < count; base += 32) {
@@ -327,43 +432,7 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
         }
         my = my_next;
       }
-      acc = kahan_result(acc, comp);
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) {
-        acc.x += __shfl_xor_sync(kFull, acc.x, off);
-        acc.y += __shfl_xor_sync(kFull, acc.y, off);
-        acc.z += __shfl_xor_sync(kFull, acc.z, off);
-        acc.w += __shfl_xor_sync(kFull, acc.w, off);
-      }
-      if (single) {
-        if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, acc);
-      } else {
-        if (g == 0 && active)
-          __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
-        __threadfence();
-        __syncwarp();
-        int prev = 0;
-        if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
-        prev = __shfl_sync(kFull, prev, 0);
-        if (prev == hr.nchunks - 1) {   // this warp is the last chunk of the row to finish
-          __threadfence();
-          if (g == 0 && active && !raw_out) yown = __ldcs(a.yo + (size_t)hr.row * ld4 + c4);
-          float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
-          for (int k = g; k < hr.nchunks; k += G)
-            if (active)
-              kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
-          tot = kahan_result(tot, tcomp);
-#pragma unroll
-          for (int off = LPR; off < 32; off <<= 1) {
-            tot.x += __shfl_xor_sync(kFull, tot.x, off);
-            tot.y += __shfl_xor_sync(kFull, tot.y, off);
-            tot.z += __shfl_xor_sync(kFull, tot.z, off);
-            tot.w += __shfl_xor_sync(kFull, tot.w, off);
-          }
-          if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, tot);
-          if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
-        }
-      }
+      own.finish_chunk(hr, ch, kahan_result(acc, comp), yown);
     }
   }
 
@@ -411,7 +480,7 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
       const int32_t* ridx = item_idx(it0);
       const int maxdeg = __reduce_max_sync(kFull, deg);
       float4 yown = hge_f4_zero();
-      if (valid && active && !raw_out) yown = __ldcs(a.yo + (size_t)row * ld4 + c4);
+      if (valid && active && !raw_out) yown = own.load_own(row);
 
       float4 acc = hge_f4_zero(), comp = hge_f4_zero();
       for (int base = 0; base < maxdeg; base += 8) {
@@ -431,7 +500,7 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
 #pragma unroll
         for (int k = 0; k < K; ++k) cur[k] = nxt[k];
       }
-      if (valid && active) finish_row(row, (float)deg, invs, yown, kahan_result(acc, comp));
+      if (valid && active) own.finish_row(row, (float)deg, invs, yown, kahan_result(acc, comp));
       it0 = it1;
       it1 = it2;
 #pragma unroll
@@ -439,43 +508,142 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
     }
   }
 
-  if (raw_out) return;
-
-  // ---- per-column min / max of the rows this block produced ---------------------------
-#pragma unroll
-  for (int off = LPR; off < 32; off <<= 1) {
-    vmin.x = fminf(vmin.x, __shfl_xor_sync(kFull, vmin.x, off));
-    vmin.y = fminf(vmin.y, __shfl_xor_sync(kFull, vmin.y, off));
-    vmin.z = fminf(vmin.z, __shfl_xor_sync(kFull, vmin.z, off));
-    vmin.w = fminf(vmin.w, __shfl_xor_sync(kFull, vmin.w, off));
-    vmax.x = fmaxf(vmax.x, __shfl_xor_sync(kFull, vmax.x, off));
-    vmax.y = fmaxf(vmax.y, __shfl_xor_sync(kFull, vmax.y, off));
-    vmax.z = fmaxf(vmax.z, __shfl_xor_sync(kFull, vmax.z, off));
-    vmax.w = fmaxf(vmax.w, __shfl_xor_sync(kFull, vmax.w, off));
-  }
   __shared__ float4 smin[kWarps][LPR];
   __shared__ float4 smax[kWarps][LPR];
-  if (g == 0) {
-    smin[warp][gl] = vmin;
-    smax[warp][gl] = vmax;
+  own.template publish_minmax<kWarps>(smin, smax);
+}
+
+// ----------------------------------------------------------------------------------------
+// long rows through the bulk-copy engine (TMA, non-tensor form)
+// ----------------------------------------------------------------------------------------
+// The register-based gather above can keep at most (resident warps x 8 x 512 B) in flight per
+// SM, bounded by the register file.  Here every lane hands one gathered row to the bulk-copy
+// engine (cp.async.bulk global -> shared, completion counted on an mbarrier): a warp-wide
+// instruction requests 32 rows, the rows land in a per-warp ring of STAGES x 32 row buffers in
+// shared memory, and the warp only reads them back (conflict-free LDS.128) to add them up.
+// In flight per SM: WARPS x (STAGES - 1) x 32 rows, bounded by the 227 KB of shared memory
+// instead of registers.
+// MEASURED (profiles/r1_bulk_copy_experiment.md): slower than the register gather for 128-byte
+// rows -- UBLKCP takes uniform-register operands, so the 32 per-lane copies of a warp are
+// issued one after the other, and the copy engine sustains about one 128-byte request per
+// ~40 cycles per SM.  Config 2: 0.607 vs 0.478 ms per sweep; config 5 on one GPU: 6.0 vs
+// 2.9 s per step.  Kept as an opt-in (hge_ctx_set_bulk) for wide rows; off by default.
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
   }
-  __syncthreads();
-  if (threadIdx.x < LPR * 4) {
-    const int l = threadIdx.x >> 2, j = threadIdx.x & 3;
-    const int col = (slab * LPR + l) * 4 + j;
-    if (col < a.R) {
-      float lo = inf, hi = -inf;
+}
+__device__ __forceinline__ void bulk_row_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int LPR, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_heavy_bulk(const HalfSweepArgs a) {
+  constexpr int G = 32 / LPR;
+  constexpr int ROW4 = LPR;                          // float4 slots per staged row
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  RowOwner<LPR> own(a);
+  const int lane = own.lane, gl = own.gl, g = own.g, ld4 = own.ld4;
+  const bool active = own.active, raw_out = own.raw_out;
+  float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)own.warp * STAGES * 32 * ROW4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * STAGES * 32 * ROW4 * 16) +
+                   own.warp * STAGES;
+  if (lane == 0) {
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        lo = fminf(lo, reinterpret_cast<const float*>(&smin[w][l])[j]);
-        hi = fmaxf(hi, reinterpret_cast<const float*>(&smax[w][l])[j]);
-      }
-      if (lo <= hi) {  // this block produced at least one row
-        atomicMin(a.mm_cur + col, hge_enc(lo));
-        atomicMax(a.mm_cur + ld4 * 4 + col, hge_enc(hi));
-      }
-    }
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();
+  const int row_f4 = min(LPR, ld4 - own.slab * LPR);   // float4 of a row in this column slab
+  const uint32_t row_bytes = (uint32_t)row_f4 * 16u;
+  uint32_t parity = 0;                                 // bit s: phase of stage s
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + own.warp;
+  const int64_t nw = (int64_t)gridDim.x * WARPS;
+
+  for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
+    const int2 ch = a.chunks[ci];
+    const HgeHeavyRow hr = a.hrows[ch.x];
+    const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
+    const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
+    const int32_t* cidx = a.idx + start;
+    const int nblk = (count + 31) >> 5;
+    float4 yown = hge_f4_zero();
+    if (hr.nchunks == 1 && g == 0 && active && !raw_out) yown = own.load_own(hr.row);
+
+    // hand block b (32 incidences) to the copy engine; `col` is this lane's column id of it
+    auto issue = [&](int b, int col) {
+      const int s = b % STAGES;
+      const int valid = min(32, count - b * 32);
+      if (lane == 0) mbar_expect_tx(bars + s, (uint32_t)valid * row_bytes);
+      __syncwarp();
+      if (col >= 0)
+        bulk_row_g2s(ring + ((size_t)s * 32 + lane) * ROW4,
+                     a.yg + (size_t)col * ld4 + own.slab * LPR, row_bytes, bars + s);
+    };
+    auto load_col = [&](int b) -> int {
+      return (b < nblk && b * 32 + lane < count) ? __ldcs(cidx + b * 32 + lane) : -1;
+    };
+
+    int col_next = load_col(0);
+#pragma unroll 1
+    for (int b = 0; b < STAGES - 1 && b < nblk; ++b) {
+      const int col = col_next;
+      col_next = load_col(b + 1);
+      issue(b, col);
+    }
+    float4 acc = hge_f4_zero();
+    for (int b = 0; b < nblk; ++b) {
+      const int ahead = b + STAGES - 1;
+      if (ahead < nblk) {
+        const int col = col_next;
+        col_next = load_col(ahead + 1);
+        issue(ahead, col);
+      }
+      const int s = b % STAGES;
+      mbar_wait(bars + s, (parity >> s) & 1u);
+      parity ^= 1u << s;
+      const float4* stage = ring + (size_t)s * 32 * ROW4;
+      const int valid = min(32, count - b * 32);
+#pragma unroll
+      for (int r = 0; r < LPR; ++r) {
+        const int t = r * G + g;
+        if (t < valid && active) hge_f4_add(acc, stage[(size_t)t * ROW4 + gl]);
+      }
+      __syncwarp();   // every lane has read stage s before it is handed out again
+    }
+    own.finish_chunk(hr, ch, acc, yown);
+  }
+
+  float4(*smin)[LPR] = reinterpret_cast<float4(*)[LPR]>(smem_raw);
+  float4(*smax)[LPR] = smin + WARPS;
+  __syncthreads();    // all rings are idle; reuse the front of shared memory for the reduction
+  own.template publish_minmax<WARPS>(smin, smax);
 }
 
 // Sharded edge half, second part: the raw sums have been all-reduced over the shards.
@@ -685,10 +853,37 @@ void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays
 namespace {
 
 template <int LPR>
-int launch_half(hge_algdist* st, const HalfSweepArgs& a) {
+struct BulkConfig {
+  static constexpr int kWarpsPerBlock = (LPR == 32) ? 4 : 8;
+  static constexpr int kStages = (LPR <= 8) ? 6 : 3;
+  static constexpr size_t kSmem =
+      (size_t)kWarpsPerBlock * kStages * 32 * LPR * 16 + (size_t)kWarpsPerBlock * kStages * 8;
+};
+
+template <int LPR>
+int launch_half(hge_algdist* st, HalfSweepArgs a) {
+  hge_ctx* ctx = st->ctx;
+  a.skip_heavy = 0;
+  if (ctx->use_bulk && a.n_chunks > 0) {
+    // long rows: bulk-copy kernel, one block per SM; short rows: the register gather below
+    using Cfg = BulkConfig<LPR>;
+    auto kernel = k_heavy_bulk<LPR, Cfg::kWarpsPerBlock, Cfg::kStages>;
+    static bool configured = false;
+    if (!configured) {
+      HGE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::kSmem));
+      configured = true;
+    }
+    const int blocks = (int)std::min<int64_t>(
+        ctx->num_sms, ((int64_t)a.n_chunks + Cfg::kWarpsPerBlock - 1) / Cfg::kWarpsPerBlock);
+    kernel<<<dim3(blocks, st->slabs), Cfg::kWarpsPerBlock * 32, Cfg::kSmem, ctx->stream>>>(a);
+    HGE_CHECK_LAUNCH(ctx);
+    a.skip_heavy = 1;
+    if (a.n_light == 0) return HGE_OK;
+  }
   dim3 grid(st->grid, st->slabs);
-  k_half_sweep<LPR><<<grid, kBlock, 0, st->ctx->stream>>>(a);
-  HGE_CHECK_LAUNCH(st->ctx);
+  k_half_sweep<LPR><<<grid, kBlock, 0, ctx->stream>>>(a);
+  HGE_CHECK_LAUNCH(ctx);
   return HGE_OK;
 }
 

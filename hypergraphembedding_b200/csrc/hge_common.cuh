@@ -50,6 +50,7 @@ struct hge_ctx {
   int light_max_deg;
   int chunk;
   int blocks_per_sm;
+  int use_bulk;          // long rows through the bulk-copy engine (k_heavy_bulk)
   int64_t launches;
   // pinned staging arena (bump allocation; chunks are kept for re-use)
   void* pinned_chunk[32];

@@ -1,5 +1,6 @@
 // Context, error reporting and versioning of libhge_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -87,6 +88,9 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->light_max_deg = 64;
   ctx->chunk = 512;
   ctx->blocks_per_sm = 0;  // 0: ask the occupancy calculator
+  // measured slower than the register gather (profiles/r1_bulk_copy_experiment.md): opt-in
+  ctx->use_bulk = 0;
+  if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;
   ctx->launches = 0;
   ctx->pinned_chunks = 0;
   ctx->pinned_cur = 0;
@@ -146,6 +150,12 @@ int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_pe
   if (light_max_deg) ctx->light_max_deg = light_max_deg;
   if (chunk) ctx->chunk = chunk;
   ctx->blocks_per_sm = blocks_per_sm;
+  return HGE_OK;
+}
+
+int hge_ctx_set_bulk(hge_ctx* ctx, int enabled) {
+  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_bulk: ctx is NULL");
+  ctx->use_bulk = enabled != 0;
   return HGE_OK;
 }
 

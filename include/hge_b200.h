@@ -62,6 +62,11 @@ int hge_ctx_sync(hge_ctx* ctx);
  *   chunk          incidences per warp work item for longer rows
  *   blocks_per_sm  persistent grid size = SMs * blocks_per_sm */
 int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_per_sm);
+/* Experimental: gather the long rows (more than light_max_deg incidences) through the
+ * bulk-copy engine (cp.async.bulk into a shared-memory ring, k_heavy_bulk) instead of the
+ * register gather of k_half_sweep.  Same results; measured slower for 128-byte rows
+ * (profiles/r1_bulk_copy_experiment.md), so it is off by default. */
+int hge_ctx_set_bulk(hge_ctx* ctx, int enabled);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hge_ctx_launch_count(const hge_ctx* ctx);
 
