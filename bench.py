@@ -46,6 +46,12 @@ WORKLOADS = {
                name="Friendster-community-shaped synthetic hypergraph 65M nodes / 1M edges / 1.8B incidences, R=32, 20 sweeps"),
     "c5mini": dict(kind="community", num_nodes=650000, num_edges=10000, num_incidences=18000000,
                    R=32, sweeps=20, seed=99, name="1/100-scale config 5 (debug)"),
+    # BASELINE.json configs[3]: FOBE sample generation at 10M nodes (host RNG replay; side line)
+    "c4": dict(kind="fobe", num_nodes=10000000, num_edges=5000000, seed=2024, k=5, num_samples=200,
+               name="FOBE (HG2V_BOOLEAN) sample generation, synthetic Zipf hypergraph 10M nodes / 5M edges, "
+                    "num_neighbors=5, num_samples=200"),
+    "c4mini": dict(kind="fobe", num_nodes=1000000, num_edges=500000, seed=2024, k=5, num_samples=200,
+                   name="1/10-scale config 4 (debug)"),
     # small variant for quick checks (not a bench line)
     "mini": dict(kind="power_law", num_nodes=100000, num_edges=50000, num_incidences=1000000,
                  R=32, sweeps=20, seed=1234, name="1/10-scale config 2 (debug)"),
@@ -303,6 +309,76 @@ def pair_weighting_extra(ctx, num_pairs=100000000):
           "relaxation_ms_20_sweeps": relax_ms,
           "relaxation_nnz_R_iters_per_s": A.nnz * R * sweeps / (relax_ms * 1e-3),
           "generate_s": gen_s}
+
+
+def run_fobe(args, spec):
+  """--workload c4: BooleanSamples on the 10M-node hypergraph, streamed in row chunks (the full
+  result is ~1e9 records).  First the sub-hypergraph induced by the first 100 000 nodes is
+  sampled and compared with the committed digest of the scipy / numpy oracle
+  (tests/golden/boolean_c4.npz), then the full size is timed.  FOBE probabilities are all 1, so
+  this workload has no device arithmetic: the cost is the sequential replay of numpy's MT19937
+  stream (one draw per candidate of every product row) on one host thread, with the candidate
+  rows built ahead by worker threads."""
+  import hashlib
+  from hypergraphembedding_b200 import synthetic
+  from hypergraphembedding_b200.hg2v_sample import BooleanSamplesCsr, _Graph
+  if int(os.environ.get("RANK", "0")) != 0:
+    return
+  t = time.time()
+  A = synthetic.zipf_hypergraph(spec["num_nodes"], spec["num_edges"], seed=spec["seed"])
+  gen_s = time.time() - t
+  log("generated %s in %.1f s: %d incidences" % (spec["name"], gen_s, A.nnz))
+  k, num_samples = spec["k"], spec["num_samples"]
+
+  def digest(cols, keys):
+    h = hashlib.sha256()
+    for key in keys:
+      h.update(np.ascontiguousarray(getattr(cols, key), dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+  parity = None
+  golden_path = os.path.join(ROOT, "tests", "golden", "boolean_c4.npz")
+  if spec["num_nodes"] == 10000000 and os.path.exists(golden_path):
+    g = np.load(golden_path)
+    if "induced_count" in g.files:
+      sub = synthetic.induced_on_first_nodes(A, 100000)
+      np.random.seed(int(g["seed"]))
+      out = BooleanSamplesCsr(sub, k, num_samples)
+      parity = {"case": "sub-hypergraph induced by the first 100000 nodes vs scipy/numpy oracle digest",
+                "records": len(out),
+                "bit_exact": bool(len(out) == int(g["induced_count"]) and
+                                  digest(out, ("left_node", "left_edge", "right_node", "right_edge")) ==
+                                  str(g["induced_index_sha"]) and
+                                  digest(out, ("neigh_node", "neigh_edge")) == str(g["induced_neigh_sha"]))}
+      del out
+  t = time.time()
+  graph = _Graph.from_csr(A)
+  prep_s = time.time() - t
+  secs, records, check = [], 0, 0
+  for step in range(max(1, args.steps)):
+    np.random.seed(0)
+    t = time.time()
+    records, check = 0, 0
+    for part in BooleanSamplesCsr(graph, k, num_samples, chunk_rows=262144, stream=True):
+      records += len(part)
+      check ^= int(np.bitwise_xor.reduce(part.left_node.astype(np.int64) * 1000003 +
+                                         part.right_node.astype(np.int64) * 10007 +
+                                         part.left_edge.astype(np.int64) * 101 +
+                                         part.right_edge.astype(np.int64))) if len(part) else 0
+    secs.append(time.time() - t)
+    log("step %d: %d records in %.1f s" % (step, records, secs[-1]))
+  best = min(secs)
+  out = {"metric": "FOBE samples/sec", "value": records / best, "unit": "samples/s", "n_gpus": args.gpus,
+         "steps": len(secs), "warmup": 0, "ms_per_step": best * 1e3, "higher_is_better": True,
+         "scaling": "replicas only", "vs_baseline": None, "dtype": "int32/uint32", "data": "synthetic",
+         "config": {"workload": spec["name"], "nodes": int(A.shape[0]), "edges": int(A.shape[1]),
+                    "nnz": int(A.nnz), "seed": spec["seed"], "records": records,
+                    "xor_checksum": check, "generate_s": gen_s, "transpose_s": prep_s,
+                    "host_threads": os.cpu_count(), "parity": parity},
+         "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": 0,
+         "note": "host-only workload: every FOBE probability is 1, the work is numpy's sequential "
+                 "MT19937 stream replayed bit-exactly (DESIGN.md section 4)"}
+  print(json.dumps(out), flush=True)
 
 
 def run_ours(args, spec):
@@ -775,7 +851,9 @@ def main():
                   help="edge slices of the sharded edge half (overlap of all-reduce and gather)")
   args = ap.parse_args()
   spec = WORKLOADS[args.workload]
-  if args.impl == "reference":
+  if spec["kind"] == "fobe":
+    run_fobe(args, spec)
+  elif args.impl == "reference":
     run_reference(args, spec)
   else:
     run_ours(args, spec)

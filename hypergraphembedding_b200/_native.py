@@ -106,6 +106,7 @@ SIGNATURES = {
                                            ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int64,
                                            c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp,
                                            ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "hge_sampler_set_threads": (ctypes.c_int, [ctypes.c_int]),
     "hge_sample_neighbors": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64,
                                             ctypes.c_int, c_vp, c_vp, c_vp]),
 }

@@ -63,21 +63,25 @@ class SampleColumns(collections.abc.Sequence):
   def build(cls, num_neighbors, count, left_node=None, left_edge=None, right_node=None,
             right_edge=None, neigh_node=None, neigh_edge=None, nn_prob=None, ee_prob=None,
             ne_prob=None):
+    # absent columns are constant read-only views (no memory): a chunk of a streamed 1e9-record
+    # result only pays for the columns it has; concatenate() materialises them
     def idx(a):
-      return np.full(count, NONE_IDX, np.int32) if a is None else np.asarray(a, dtype=np.int32)
+      return (np.broadcast_to(np.int32(NONE_IDX), (count,)) if a is None
+              else np.asarray(a, dtype=np.int32))
 
     def prob(a):
-      return np.full(count, np.nan, np.float32) if a is None else np.asarray(a, dtype=np.float32)
+      return (np.broadcast_to(np.float32(np.nan), (count,)) if a is None
+              else np.asarray(a, dtype=np.float32))
 
     k = int(num_neighbors)
     has = neigh_node is not None
-    none = np.full((count, k), NONE_IDX, np.int32)
+    none = np.broadcast_to(np.int32(NONE_IDX), (count, k))
     return cls(k, left_node=idx(left_node), left_edge=idx(left_edge), right_node=idx(right_node),
                right_edge=idx(right_edge),
                neigh_node=np.asarray(neigh_node, np.int32).reshape(count, k) if has else none,
-               neigh_edge=np.asarray(neigh_edge, np.int32).reshape(count, k) if has else none.copy(),
+               neigh_edge=np.asarray(neigh_edge, np.int32).reshape(count, k) if has else none,
                nn_prob=prob(nn_prob), ee_prob=prob(ee_prob), ne_prob=prob(ne_prob),
-               has_neighbors=np.full(count, has, dtype=bool))
+               has_neighbors=np.broadcast_to(np.bool_(has), (count,)))
 
   @classmethod
   def concatenate(cls, parts):
@@ -170,36 +174,60 @@ def _alpha_scale(val, alpha=0):
 
 
 class _Graph(object):
-  """Host CSR arrays of a hypergraph proto the way the samplers see it: A from ``node.edges``
+  """Host CSR arrays of a hypergraph the way the samplers see it: A from ``node.edges``
   (ToCsrMatrix), B from ``edge.nodes`` (ToEdgeCsrMatrix), their transposes for the products
   ``A * A.T`` / ``B * B.T``, and the proto-map iteration orders."""
 
   def __init__(self, hypergraph):
     A = ToCsrMatrix(hypergraph)
     B = ToEdgeCsrMatrix(hypergraph)
+    self._set(A, B, list(hypergraph.node), list(hypergraph.edge))
+
+  @classmethod
+  def from_csr(cls, A, B=None, node_rows=None, edge_rows=None):
+    """The same view of a hypergraph given as a canonical N x E incidence CSR (and optionally
+    the E x N CSR of ``edge.nodes``; default: the transpose).  Row orders default to ascending
+    ids, which is the proto-map order for dense ids."""
+    g = cls.__new__(cls)
+    A = sps.csr_matrix(A)
+    if B is None:
+      B = A.T.tocsr()
+      B.sort_indices()
+    g._set(A, sps.csr_matrix(B),
+           np.arange(A.shape[0], dtype=np.int32) if node_rows is None else node_rows,
+           np.arange(A.shape[1], dtype=np.int32) if edge_rows is None else edge_rows)
+    return g
+
+  def _set(self, A, B, node_rows, edge_rows):
     n = max(A.shape[0], B.shape[1])
     e = max(A.shape[1], B.shape[0])
     A = sps.csr_matrix((A.data, A.indices, _pad(A.indptr, n)), shape=(n, e))
     B = sps.csr_matrix((B.data, B.indices, _pad(B.indptr, e)), shape=(e, n))
-    At = A.T.tocsr()
-    At.sort_indices()
-    consistent = (At.nnz == B.nnz and np.array_equal(At.indptr, B.indptr) and
-                  np.array_equal(At.indices, B.indices))
     self.A, self.B = A, B
     self.a, self.b = _native.CsrArrays(A), _native.CsrArrays(B)
+    consistent = A.nnz == B.nnz and _is_transpose(self.a, self.b)
     if consistent:
       self.at, self.bt = self.b, self.a
     else:
+      At = A.T.tocsr()
+      At.sort_indices()
       Bt = B.T.tocsr()
       Bt.sort_indices()
       self.at, self.bt = _native.CsrArrays(At), _native.CsrArrays(Bt)
-    self.node_rows = list(hypergraph.node)
-    self.edge_rows = list(hypergraph.edge)
+    self.node_rows = node_rows
+    self.edge_rows = edge_rows
     self.num_nodes, self.num_edges = n, e
 
   def incidence(self, ctx):
     return _native.Incidence(ctx, self.num_nodes, self.num_edges, self.a.ptr, self.a.idx,
                              self.b.ptr, self.b.idx)
+
+
+def _is_transpose(a, b):
+  """True when the canonical CSR `b` is the transpose of the canonical CSR `a`."""
+  At = sps.csr_matrix((np.ones(len(a.idx), dtype=np.int8), a.idx, a.ptr), shape=a.shape).T.tocsr()
+  At.sort_indices()
+  return bool(np.array_equal(At.indptr, b.ptr) and np.array_equal(At.indices, b.idx))
 
 
 def _pad(indptr, rows):
@@ -232,6 +260,78 @@ def embedding_to_arrays(embedding, num_nodes, num_edges):
 ################################################################################
 
 
+def _row_chunks(rows, samples, chunk_rows):
+  rows = np.asarray(rows, dtype=np.int32)
+  samples = np.asarray(samples, dtype=np.int32)
+  assert len(samples) == len(rows)
+  assert len(samples) > 0          # hg2v_sample.py:67
+  step = len(rows) if not chunk_rows else int(chunk_rows)
+  for lo in range(0, len(rows), step):
+    yield rows[lo:lo + step], samples[lo:lo + step]
+
+
+def _boolean_sample_chunks(g, k, node_samples, edge_samples, neg_node_samples, neg_edge_samples,
+                           state, chunk_rows=0):
+  """BooleanSamples as a stream of SampleColumns chunks in the reference's record order.  The
+  RNG stream is consumed row after row exactly as one call over all rows would consume it, so
+  the concatenation of the chunks does not depend on `chunk_rows` (0 = one chunk per phase)."""
+  ones = lambda m: np.broadcast_to(np.float32(1.0), (m,))
+
+  def same_type(mats, rows, samples, left, right, prob, negative=False):
+    for r_rows, r_samples in _row_chunks(rows, samples, chunk_rows):
+      r, c = _native.sample_adj_rows(mats, r_rows, r_samples, state, negative=negative)
+      cols = {left: r, right: c}
+      if prob and not negative:
+        cols[prob] = ones(len(r))
+      yield SampleColumns.build(k, len(r), **cols)
+
+  def node_edge(node_s, edge_s, negative=False):
+    # all (node, edge) pairs are drawn first (node rows, then edge rows), then the neighbour
+    # arrays of every pair in that order (hg2v_sample.py:170-195)
+    pairs_n, pairs_e = [], []
+    for r_rows, r_samples in _row_chunks(g.node_rows, node_s, chunk_rows):
+      n1, e1 = _native.sample_adj_rows((g.a,), r_rows, r_samples, state, negative=negative)
+      pairs_n.append(n1)
+      pairs_e.append(e1)
+    for r_rows, r_samples in _row_chunks(g.edge_rows, edge_s, chunk_rows):
+      e2, n2 = _native.sample_adj_rows((g.b,), r_rows, r_samples, state, negative=negative)
+      pairs_n.append(n2)
+      pairs_e.append(e2)
+    nodes, edges = np.concatenate(pairs_n), np.concatenate(pairs_e)
+    step = len(nodes) if not chunk_rows else max(1, int(chunk_rows) * 8)
+    for lo in range(0, max(len(nodes), 1), max(step, 1)):
+      sn, se = nodes[lo:lo + step], edges[lo:lo + step]
+      nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, sn, se, k, state)
+      cols = dict(left_node=sn, right_edge=se, neigh_node=nbr_n, neigh_edge=nbr_e)
+      if not negative:
+        cols["ne_prob"] = ones(len(sn))
+      yield SampleColumns.build(k, len(sn), **cols)
+
+  log.info("Sampling node-node probabilities")
+  for part in same_type((g.a, g.at), g.node_rows, node_samples, "left_node", "right_node", "nn_prob"):
+    yield part
+  log.info("Sampling edge-edge probabilities")
+  for part in same_type((g.b, g.bt), g.edge_rows, edge_samples, "left_edge", "right_edge", "ee_prob"):
+    yield part
+  log.info("Getting node-edge / edge-node relationships")
+  for part in node_edge(node_samples, edge_samples):
+    yield part
+
+  if neg_node_samples is not None:
+    log.info("Node-Node Negatives")
+    for part in same_type((g.a, g.at), g.node_rows, neg_node_samples, "left_node", "right_node",
+                          None, negative=True):
+      yield part
+    for label in ("Edge-Edge Negatives", "Node-Edge Negatives"):   # sic: both are edge-edge
+      log.info(label)
+      for part in same_type((g.b, g.bt), g.edge_rows, neg_edge_samples, "left_edge", "right_edge",
+                            None, negative=True):
+        yield part
+    log.info("Getting node-edge / edge-node negatives")
+    for part in node_edge(neg_node_samples, neg_edge_samples, negative=True):
+      yield part
+
+
 def BooleanSamples(hypergraph, num_neighbors, num_samples, neg_samples=0, disable_pbar=False):
   """hg2v_sample.py:125-242 (FOBE): up to num_samples node-node, edge-edge and node-edge /
   edge-node first-order samples per row with probability 1, optionally neg_samples uniform
@@ -241,49 +341,45 @@ def BooleanSamples(hypergraph, num_neighbors, num_samples, neg_samples=0, disabl
   edge_samples = [int(edge.weight * num_samples) for _, edge in hypergraph.edge.items()]
   neg_node_samples = [int(node.weight * neg_samples) for _, node in hypergraph.node.items()]
   neg_edge_samples = [int(edge.weight * neg_samples) for _, edge in hypergraph.edge.items()]
-
   g = _Graph(hypergraph)
-  k = num_neighbors
   state = _native.LegacyRngState()
-  parts = []
-
-  log.info("Sampling node-node probabilities")
-  r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, node_samples, state)
-  parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c,
-                                   nn_prob=np.ones(len(r), np.float32)))
-  log.info("Sampling edge-edge probabilities")
-  r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, edge_samples, state)
-  parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c,
-                                   ee_prob=np.ones(len(r), np.float32)))
-  log.info("Getting node-edge relationships")
-  n1, e1 = _native.sample_adj_rows((g.a,), g.node_rows, node_samples, state)
-  log.info("Getting edge-node relationships")
-  e2, n2 = _native.sample_adj_rows((g.b,), g.edge_rows, edge_samples, state)
-  nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
-  nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state)
-  parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
-                                   neigh_node=nbr_n, neigh_edge=nbr_e,
-                                   ne_prob=np.ones(len(nodes), np.float32)))
-
-  if neg_samples > 0:
-    log.info("Node-Node Negatives")
-    r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, neg_node_samples, state, negative=True)
-    parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c))
-    for label in ("Edge-Edge Negatives", "Node-Edge Negatives"):   # sic: both are edge-edge
-      log.info(label)
-      r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, neg_edge_samples, state,
-                                     negative=True)
-      parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c))
-    log.info("Getting node-edge negatives")
-    n1, e1 = _native.sample_adj_rows((g.a,), g.node_rows, neg_node_samples, state, negative=True)
-    log.info("Getting edge-node negatives")
-    e2, n2 = _native.sample_adj_rows((g.b,), g.edge_rows, neg_edge_samples, state, negative=True)
-    nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
-    nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state)
-    parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
-                                     neigh_node=nbr_n, neigh_edge=nbr_e))
+  parts = list(_boolean_sample_chunks(g, num_neighbors, node_samples, edge_samples,
+                                      neg_node_samples if neg_samples > 0 else None,
+                                      neg_edge_samples if neg_samples > 0 else None, state))
   state.commit()
   return SampleColumns.concatenate(parts)
+
+
+def BooleanSamplesCsr(incidence, num_neighbors, num_samples, neg_samples=0, node_weights=None,
+                      edge_weights=None, chunk_rows=0, stream=False):
+  """BooleanSamples on a canonical N x E incidence CSR instead of a proto (the 10M-node case of
+  BASELINE.json configs[3]: building the proto alone would take minutes of Python).  Same
+  records, same RNG consumption as BooleanSamples on the equivalent proto with dense ids.
+  With ``stream=True`` returns an iterator of SampleColumns chunks of about `chunk_rows` rows
+  (record order preserved) that commits the RNG state when exhausted; otherwise one
+  SampleColumns."""
+  g = incidence if isinstance(incidence, _Graph) else _Graph.from_csr(incidence)
+
+  def per_row(weights, count, base):
+    if weights is None:
+      return np.full(count, int(base), dtype=np.int32)
+    return np.asarray([int(w * base) for w in weights], dtype=np.int32)
+
+  node_samples = per_row(node_weights, len(g.node_rows), num_samples)
+  edge_samples = per_row(edge_weights, len(g.edge_rows), num_samples)
+  neg_node = per_row(node_weights, len(g.node_rows), neg_samples) if neg_samples > 0 else None
+  neg_edge = per_row(edge_weights, len(g.edge_rows), neg_samples) if neg_samples > 0 else None
+  state = _native.LegacyRngState()
+
+  def chunks():
+    for part in _boolean_sample_chunks(g, num_neighbors, node_samples, edge_samples, neg_node,
+                                       neg_edge, state, chunk_rows=chunk_rows):
+      yield part
+    state.commit()
+
+  if stream:
+    return chunks()
+  return SampleColumns.concatenate(list(chunks()))
 
 
 ################################################################################

@@ -98,6 +98,51 @@ def community_hypergraph(num_nodes, num_edges, num_incidences, size_exponent=1.5
   return _to_csr(n, e, num_nodes, num_edges)
 
 
+def zipf_hypergraph(num_nodes=10000000, num_edges=5000000, zipf_exponent=2.2, max_degree=1000,
+                    edge_exponent=0.5, max_edge_size=1000, seed=2024):
+  """Config 4 family (FOBE sampling at scale): node degree ~ Zipf(a) >= 1 capped at
+  `max_degree`, edges drawn ~ (rank+1)^-b with the edge size capped at `max_edge_size` (members
+  beyond the cap are re-drawn uniformly), which keeps sum(size^2) -- the size of the candidate
+  rows of A * A.T -- bounded; every edge non-empty; ids shuffled."""
+  rng = np.random.Generator(np.random.PCG64(seed))
+  deg = np.minimum(rng.zipf(zipf_exponent, num_nodes), max_degree).astype(np.int64)
+  n = np.repeat(np.arange(num_nodes, dtype=np.int64), deg)
+  cdf = np.cumsum(_power_law_probs(num_edges, edge_exponent))
+  cdf[-1] = 1.0
+  e = np.minimum(_draw(rng, cdf, len(n)), num_edges - 1)
+  for _ in range(8):
+    sizes = np.bincount(e, minlength=num_edges)
+    if sizes.max() <= max_edge_size:
+      break
+    # rank of every incidence inside its edge; those beyond the cap move to a uniform edge
+    order = np.argsort(e, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(sizes)])[:-1]
+    rank = np.empty(len(e), dtype=np.int64)
+    rank[order] = np.arange(len(e), dtype=np.int64) - np.repeat(starts, sizes)
+    over = np.nonzero(rank >= max_edge_size)[0]
+    e[over] = rng.integers(0, num_edges, len(over))
+  iso_e = np.nonzero(np.bincount(e, minlength=num_edges) == 0)[0]
+  n = np.concatenate([n, rng.integers(0, num_nodes, len(iso_e))])
+  e = np.concatenate([e, iso_e])
+  node_perm = rng.permutation(num_nodes)
+  edge_perm = rng.permutation(num_edges)
+  return _to_csr(node_perm[n], edge_perm[e], num_nodes, num_edges)
+
+
+def induced_on_first_nodes(A, num_nodes):
+  """Sub-hypergraph induced by nodes [0, num_nodes): their rows, and only the edges they touch,
+  relabelled densely in ascending id order (what CompressRange would produce).  Returns the
+  canonical CSR."""
+  sub = sps.csr_matrix(A)[:num_nodes]
+  used = np.unique(sub.indices)
+  relabel = np.full(A.shape[1], -1, dtype=np.int64)
+  relabel[used] = np.arange(len(used))
+  m = sps.csr_matrix((np.ones(sub.nnz, dtype=bool), relabel[sub.indices].astype(np.int32),
+                      sub.indptr), shape=(num_nodes, len(used)))
+  m.sort_indices()
+  return m
+
+
 def _to_csr(n, e, num_nodes, num_edges):
   m = sps.csr_matrix((np.ones(len(n), dtype=bool), (n, e)), shape=(num_nodes, num_edges),
                      dtype=bool)

@@ -236,6 +236,11 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
                         uint32_t* state625, int32_t* out_row, int32_t* out_col, int64_t capacity,
                         int64_t* out_count);
 
+/* Worker threads that build candidate rows ahead of the (sequential) draw loop of
+ * hge_sample_adj_rows: 0 = automatic (one thread for small jobs, up to 16 for >= 16K product
+ * rows; HGE_SAMPLER_THREADS overrides), 1 = build rows inline.  Results do not depend on it. */
+int hge_sampler_set_threads(int threads);
+
 /* _sample_neighbors (hg2v_sample.py:49-51) for a list of (node, edge) samples: per sample k
  * draws with replacement from the node's edges, then k from the edge's nodes
  * (hg2v_sample.py:184-187, 604-605).  Outputs are [num_samples, k]. */
