@@ -105,6 +105,20 @@ def hbm_peak():
   return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the half-sweep kernel from the
+  committed `ncu --set full` capture (profiles/half_sweep_traffic.json, written by
+  tools/ncu_summary.py); None when there is no capture of this workload."""
+  path = os.path.join(ROOT, "profiles", "half_sweep_traffic.json")
+  try:
+    d = json.load(open(path))
+    if d.get("workload") == workload:
+      return float(d["bytes_per_launch"]), d.get("source")
+  except (OSError, ValueError, KeyError):
+    pass
+  return None, None
+
+
 def init_process_group_quiet(rank, world, device):
   """torch.distributed over NCCL with stdout pointed at stderr while the communicator comes
   up: NCCL prints its version banner on stdout, and rank 0 must print exactly one JSON line."""
@@ -462,6 +476,7 @@ def run_ours(args, spec):
   bytes_per_launch = algorithmic_bytes_per_sweep(N, E, nnz, R) / 2.0
   achieved = bytes_per_launch / (mean_half_ms * 1e-3) / 1e9
   peak, peak_src = hbm_peak()
+  traffic, traffic_src = ncu_traffic(args.workload)
 
   # ---- end-to-end arm: host buffers through the C ABI --------------------------------------
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -518,7 +533,8 @@ def run_ours(args, spec):
                        % ((N + E) * R * 4 >> 20, (2 * nnz * 4) >> 20),
                  "device_vs_host_arm_identical": same},
       "roofline": {"bound": "hbm", "kernel": "k_half_sweep<8>", "achieved": achieved, "peak": peak,
-                   "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                   "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                   "traffic_source": traffic_src, "peak_source": peak_src,
                    "bytes_per_launch": bytes_per_launch, "ms_per_launch": mean_half_ms,
                    "node_half_ms": node_ms, "edge_half_ms": edge_ms,
                    "frac_of_nominal_8TBs": achieved / 8000.0},
@@ -685,6 +701,7 @@ def run_community(args, spec, world, rank, local_rank):
     }
     print(json.dumps(out), flush=True)
   if world > 1:
+    hd.release_peer_arenas(dist)
     dist.destroy_process_group()
 
 
@@ -833,6 +850,7 @@ def run_sharded(args, spec, world, rank, local_rank):
         "clocks": clocks,
     }
     print(json.dumps(out), flush=True)
+  hd.release_peer_arenas(dist)
   dist.destroy_process_group()
 
 

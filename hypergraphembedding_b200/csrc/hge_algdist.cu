@@ -41,10 +41,17 @@ __global__ void k_row_degree(int32_t rows, const int64_t* __restrict__ ptr,
     deg[r] = (int32_t)(ptr[r + 1] - ptr[r]);
 }
 
-// wsum[r] = sum_{b in row r} 1 / other_deg[b], accumulated in f64 (8 lanes per row).
+// wsum[r] = sum_{b in row r} 1 / other_deg[b], accumulated in f64.  Rows up to kWsumLong
+// incidences: 8 lanes per row.  Longer rows are only appended to `long_rows` here and summed by
+// k_row_wsum_long with one block per row: a 1e5-member edge on 8 lanes was 4.5 of the 7 ms the
+// whole incidence set-up took.  Both sums have a fixed shape, so the result is the same on
+// every run whatever order the long rows were listed in.
+constexpr int kWsumLong = 512;
+
 __global__ void k_row_wsum(int32_t rows, const int64_t* __restrict__ ptr,
                            const int32_t* __restrict__ idx,
-                           const int32_t* __restrict__ other_deg, double* __restrict__ wsum) {
+                           const int32_t* __restrict__ other_deg, double* __restrict__ wsum,
+                           int32_t* __restrict__ long_rows, int32_t* __restrict__ n_long) {
   const int sub = threadIdx.x & 7;
   const int64_t ng = (int64_t)gridDim.x * (blockDim.x >> 3);
   const int64_t g0 = blockIdx.x * (int64_t)(blockDim.x >> 3) + (threadIdx.x >> 3);
@@ -52,26 +59,56 @@ __global__ void k_row_wsum(int32_t rows, const int64_t* __restrict__ ptr,
   for (int64_t base = 0; base < rows; base += ng) {
     const int64_t r = base + g0;
     double s = 0.0;
+    bool is_long = false;
     if (r < rows) {
       const int64_t b = ptr[r], e = ptr[r + 1];
-      for (int64_t p = b + sub; p < e; p += 8) s += 1.0 / (double)other_deg[idx[p]];
+      is_long = e - b > kWsumLong;
+      if (!is_long)
+        for (int64_t p = b + sub; p < e; p += 8) s += 1.0 / (double)other_deg[idx[p]];
     }
 #pragma unroll
     for (int off = 4; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-    if (r < rows && sub == 0) wsum[r] = s;
+    if (r < rows && sub == 0) {
+      if (is_long)
+        long_rows[atomicAdd(n_long, 1)] = (int32_t)r;
+      else
+        wsum[r] = s;
+    }
   }
 }
 
-// The work items are built on the host before the inverse weight sums exist on the device;
-// these two kernels fill them in, so that incidence creation never waits for the GPU.
-__global__ void k_patch_light(int64_t n, HgeLightItem* items, const float* __restrict__ invs) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
-    if (items[i].row >= 0) items[i].invs = invs[items[i].row];
-}
-__global__ void k_patch_heavy(int32_t n, HgeHeavyRow* rows, const float* __restrict__ invs) {
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    rows[i].invs = invs[rows[i].row];
+__global__ void __launch_bounds__(kBlock) k_row_wsum_long(
+    const int32_t* __restrict__ long_rows, const int32_t* __restrict__ n_long,
+    const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+    const int32_t* __restrict__ other_deg, double* __restrict__ wsum) {
+  __shared__ double part[kWarps];
+  const int n = *n_long;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int32_t r = long_rows[i];
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;     // four independent gathers in flight
+    int64_t p = b + threadIdx.x;
+    for (; p + 3 * kBlock < e; p += 4 * kBlock) {
+      const int32_t d0 = other_deg[idx[p]], d1 = other_deg[idx[p + kBlock]];
+      const int32_t d2 = other_deg[idx[p + 2 * kBlock]], d3 = other_deg[idx[p + 3 * kBlock]];
+      s0 += 1.0 / (double)d0;
+      s1 += 1.0 / (double)d1;
+      s2 += 1.0 / (double)d2;
+      s3 += 1.0 / (double)d3;
+    }
+    for (; p < e; p += kBlock) s0 += 1.0 / (double)other_deg[idx[p]];
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kWarps; ++w) t += part[w];
+      wsum[r] = t;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void k_invert(int32_t rows, const double* __restrict__ wsum, float* __restrict__ invs) {
@@ -702,9 +739,16 @@ int grid_1d(const hge_ctx* ctx, int64_t work, int block) {
 int compute_wsum(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, const int32_t* d_idx,
                  const int32_t* d_other_deg, double** wsum) {
   HGE_TRY(hge_dev_alloc(ctx, wsum, (size_t)rows));
+  int32_t* long_rows = nullptr;   // [0] = count, [1..] = row ids
+  HGE_TRY(hge_dev_alloc(ctx, &long_rows, (size_t)rows + 1));
+  HGE_CUDA(cudaMemsetAsync(long_rows, 0, sizeof(int32_t), ctx->stream));
   k_row_wsum<<<grid_1d(ctx, (int64_t)rows * 8, kBlock), kBlock, 0, ctx->stream>>>(
-      rows, d_ptr, d_idx, d_other_deg, *wsum);
+      rows, d_ptr, d_idx, d_other_deg, *wsum, long_rows + 1, long_rows);
   HGE_CHECK_LAUNCH(ctx);
+  k_row_wsum_long<<<ctx->num_sms * 4, kBlock, 0, ctx->stream>>>(long_rows + 1, long_rows, d_ptr, d_idx,
+                                                               d_other_deg, *wsum);
+  HGE_CHECK_LAUNCH(ctx);
+  hge_dev_free(ctx, long_rows);
   return HGE_OK;
 }
 
@@ -716,132 +760,12 @@ int invert_wsum(hge_ctx* ctx, int32_t rows, const double* wsum, float** invs) {
   return HGE_OK;
 }
 
-// Work items for rows [row0, row1) of one CSR.  ptr / idx / deg / invs of `s` are set by the
-// caller (slices of the sharded edge half share them).  The items are written straight into
-// pinned memory, copied asynchronously and completed on the device (k_patch_*): no host wait.
-int build_half_schedule(hge_ctx* ctx, int32_t row0, int32_t row1,
-                        const std::vector<int64_t>& h_ptr, const char* what, HgeHalfSchedule* s) {
-  s->rows = row1 - row0;
-  s->nnz = h_ptr[row1] - h_ptr[row0];
-  s->chunk_sz = ctx->chunk;
-  const int light_max = ctx->light_max_deg;
-  const int chunk = ctx->chunk;
-
-  // pass 1: degree histogram of the short rows, list of the long rows
-  std::vector<int64_t> bucket((size_t)light_max + 2, 0);
-  std::vector<std::pair<int32_t, int32_t>> heavy;  // (deg, row)
-  int32_t max_deg = 0;
-  int64_t n_chunks = 0;
-  for (int32_t r = row0; r < row1; ++r) {
-    const int64_t d = h_ptr[r + 1] - h_ptr[r];
-    if (d <= 0) {
-      if (d < 0) {
-        hge_set_error("%s row pointers decrease at row %d", what, r);
-        return HGE_ERR_INVALID;
-      }
-      if (s->first_empty < 0) s->first_empty = r;
-    }
-    if (d > INT32_MAX) {
-      hge_set_error("%s %d has more than 2^31-1 incidences", what, r);
-      return HGE_ERR_UNSUPPORTED;
-    }
-    max_deg = std::max<int32_t>(max_deg, (int32_t)d);
-    if (d <= light_max) {
-      bucket[(size_t)d]++;
-    } else {
-      heavy.emplace_back((int32_t)d, r);
-      n_chunks += (d + chunk - 1) / chunk;
-    }
-  }
-  s->max_deg = max_deg;
-  if (n_chunks > INT32_MAX) {
-    hge_set_error("%s schedule needs more than 2^31-1 chunks", what);
-    return HGE_ERR_UNSUPPORTED;
-  }
-  // offsets: degree light_max first ... degree 0 last (longest work first)
-  std::vector<int64_t> offset((size_t)light_max + 2, 0);
-  int64_t n_light = 0;
-  for (int d = light_max; d >= 0; --d) {
-    offset[(size_t)d] = n_light;
-    n_light += bucket[(size_t)d];
-  }
-  s->n_light = n_light;
-  s->n_hrows = (int32_t)heavy.size();
-  s->n_chunks = (int32_t)n_chunks;
-
-  const size_t light_bytes = (size_t)n_light * sizeof(HgeLightItem);
-  const size_t hrow_bytes = heavy.size() * sizeof(HgeHeavyRow);
-  const size_t chunk_bytes = (size_t)n_chunks * sizeof(int2);
-  char* pinned = static_cast<char*>(hge_ctx_pinned(ctx, light_bytes + hrow_bytes + chunk_bytes + 64));
-  if (!pinned) return HGE_ERR_NOMEM;
-  HgeLightItem* light = reinterpret_cast<HgeLightItem*>(pinned);
-  HgeHeavyRow* hrows = reinterpret_cast<HgeHeavyRow*>(pinned + light_bytes);
-  int2* chunks = reinterpret_cast<int2*>(pinned + light_bytes + hrow_bytes);
-
-  // pass 2: counting sort of the short rows by descending degree
-  for (int32_t r = row0; r < row1; ++r) {
-    const int64_t d = h_ptr[r + 1] - h_ptr[r];
-    if (d > light_max) continue;
-    HgeLightItem it;
-    it.row = r;
-    it.deg_hi = (uint32_t)d | (uint32_t)((h_ptr[r] >> 32) << 8);
-    it.start_lo = (uint32_t)(h_ptr[r] & 0xffffffffll);
-    it.invs = 0.f;
-    light[offset[(size_t)d]++] = it;
-  }
-  std::sort(heavy.begin(), heavy.end(), [](const std::pair<int32_t, int32_t>& x,
-                                           const std::pair<int32_t, int32_t>& y) {
-    return x.first != y.first ? x.first > y.first : x.second < y.second;
-  });
-  int32_t n_partials = 0;
-  int64_t c = 0;
-  for (size_t h = 0; h < heavy.size(); ++h) {
-    HgeHeavyRow& hr = hrows[h];
-    hr.row = heavy[h].second;
-    hr.deg = heavy[h].first;
-    hr.start = h_ptr[hr.row];
-    hr.nchunks = (hr.deg + chunk - 1) / chunk;
-    hr.partial_base = 0;
-    if (hr.nchunks > 1) {
-      hr.partial_base = n_partials;
-      n_partials += hr.nchunks;
-    }
-    hr.invs = 0.f;
-    hr.pad = 0;
-    // the chunks of the longest rows first, so their reductions finish early
-    for (int32_t k = 0; k < hr.nchunks; ++k) chunks[c++] = make_int2((int)h, k);
-  }
-  s->n_partials = n_partials;
-
-  HGE_TRY(hge_dev_alloc(ctx, &s->light, (size_t)n_light));
-  HGE_TRY(hge_dev_alloc(ctx, &s->hrows, heavy.size()));
-  HGE_TRY(hge_dev_alloc(ctx, &s->chunks, (size_t)n_chunks));
-  if (light_bytes)
-    HGE_CUDA(cudaMemcpyAsync(s->light, light, light_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (hrow_bytes)
-    HGE_CUDA(cudaMemcpyAsync(s->hrows, hrows, hrow_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (chunk_bytes)
-    HGE_CUDA(cudaMemcpyAsync(s->chunks, chunks, chunk_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (n_light) {
-    k_patch_light<<<grid_1d(ctx, n_light, kBlock), kBlock, 0, ctx->stream>>>(n_light, s->light, s->invs);
-    HGE_CHECK_LAUNCH(ctx);
-  }
-  if (!heavy.empty()) {
-    k_patch_heavy<<<grid_1d(ctx, (int64_t)heavy.size(), kBlock), kBlock, 0, ctx->stream>>>(
-        (int32_t)heavy.size(), s->hrows, s->invs);
-    HGE_CHECK_LAUNCH(ctx);
-  }
-  return HGE_OK;
-}
-
 void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays = true) {
   if (owns_arrays) {
     hge_dev_free(ctx, s->deg);
     hge_dev_free(ctx, s->invs);
   }
-  hge_dev_free(ctx, s->light);
-  hge_dev_free(ctx, s->hrows);
-  hge_dev_free(ctx, s->chunks);
+  hge_sched_release(ctx, s);
 }
 
 }  // namespace
@@ -958,7 +882,6 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
 
   hge_incidence* inc = new (std::nothrow) hge_incidence();
   if (!inc) return HGE_ERR_NOMEM;
-  hge_ctx_pinned_reset(ctx);
   inc->ctx = ctx;
   inc->N = num_nodes;
   inc->E = num_edges;
@@ -968,50 +891,40 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
     hge_incidence_destroy(inc);
     return code;
   };
+  auto cuda_fail = [&](cudaError_t e, const char* what) {
+    hge_set_error("%s: %s failed: %s", fn, what, cudaGetErrorString(e));
+    return fail(HGE_ERR_CUDA);
+  };
 
-  inc->h_n2e_ptr.resize((size_t)num_nodes + 1);
-  inc->h_e2n_ptr.resize((size_t)num_edges + 1);
+  // Order of the queued work: row pointers first (small), then everything that needs only
+  // them -- degrees, schedule keys, sort, statistics read-back -- then the column ids (large).
+  // The one host wait of the set-up (hge_sched_finish) then overlaps the big upload.
   cudaError_t e = cudaSuccess;
+  int64_t nnz_a = 0, nnz_b = 0;
   if (mem == HGE_MEM_HOST) {
-    std::copy(n2e_ptr, n2e_ptr + num_nodes + 1, inc->h_n2e_ptr.begin());
-    std::copy(e2n_ptr, e2n_ptr + num_edges + 1, inc->h_e2n_ptr.begin());
-    const int64_t nnz_a = inc->h_n2e_ptr[num_nodes], nnz_b = inc->h_e2n_ptr[num_edges];
+    nnz_a = n2e_ptr[num_nodes];
+    nnz_b = e2n_ptr[num_edges];
+    if (n2e_ptr[0] != 0 || e2n_ptr[0] != 0 || nnz_a < 0 || nnz_b < 0) {
+      hge_set_error("%s: row pointers must start at 0 and must not decrease", fn);
+      return fail(HGE_ERR_INVALID);
+    }
     inc->owns_csr = true;
     if ((rc = hge_dev_alloc(ctx, &inc->n2e_ptr, (size_t)num_nodes + 1)) != HGE_OK) return fail(rc);
     if ((rc = hge_dev_alloc(ctx, &inc->e2n_ptr, (size_t)num_edges + 1)) != HGE_OK) return fail(rc);
     if ((rc = hge_dev_alloc(ctx, &inc->n2e_idx, (size_t)nnz_a)) != HGE_OK) return fail(rc);
     if ((rc = hge_dev_alloc(ctx, &inc->e2n_idx, (size_t)nnz_b)) != HGE_OK) return fail(rc);
-    auto up = [&](void* d, const void* h, size_t bytes) {
-      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    };
-    up(inc->n2e_ptr, n2e_ptr, ((size_t)num_nodes + 1) * 8);
-    up(inc->e2n_ptr, e2n_ptr, ((size_t)num_edges + 1) * 8);
-    up(inc->n2e_idx, n2e_idx, (size_t)nnz_a * 4);
-    up(inc->e2n_idx, e2n_idx, (size_t)nnz_b * 4);
-    if (e != cudaSuccess) {
-      hge_set_error("%s: upload failed: %s", fn, cudaGetErrorString(e));
-      return fail(HGE_ERR_CUDA);
-    }
+    e = cudaMemcpyAsync(inc->n2e_ptr, n2e_ptr, ((size_t)num_nodes + 1) * 8, cudaMemcpyHostToDevice,
+                        ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(inc->e2n_ptr, e2n_ptr, ((size_t)num_edges + 1) * 8, cudaMemcpyHostToDevice,
+                          ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "row-pointer upload");
   } else {
     inc->owns_csr = false;
     inc->n2e_ptr = const_cast<int64_t*>(n2e_ptr);
     inc->e2n_ptr = const_cast<int64_t*>(e2n_ptr);
     inc->n2e_idx = const_cast<int32_t*>(n2e_idx);
     inc->e2n_idx = const_cast<int32_t*>(e2n_idx);
-    e = cudaMemcpyAsync(inc->h_n2e_ptr.data(), n2e_ptr, ((size_t)num_nodes + 1) * 8,
-                        cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(inc->h_e2n_ptr.data(), e2n_ptr, ((size_t)num_edges + 1) * 8,
-                          cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      hge_set_error("%s: reading row pointers failed: %s", fn, cudaGetErrorString(e));
-      return fail(HGE_ERR_CUDA);
-    }
-  }
-  if (inc->h_n2e_ptr[0] != 0 || inc->h_e2n_ptr[0] != 0) {
-    hge_set_error("%s: row pointers must start at 0", fn);
-    return fail(HGE_ERR_INVALID);
   }
 
   // degrees: a neighbour's weight is 1 / (degree of that neighbour's own row),
@@ -1032,9 +945,31 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
   k_row_degree<<<grid_1d(ctx, num_edges, kBlock), kBlock, 0, ctx->stream>>>(num_edges, inc->e2n_ptr,
                                                                           eh.deg);
   ctx->launches++;
-  if (cudaGetLastError() != cudaSuccess) {
-    hge_set_error("%s: degree kernel launch failed", fn);
-    return fail(HGE_ERR_CUDA);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "degree kernel launch");
+
+  // gather schedules, phase 1 (sort by degree + statistics, asynchronous)
+  if ((rc = hge_sched_begin(ctx, 0, num_nodes, inc->n2e_ptr, num_edges, &nh)) != HGE_OK) return fail(rc);
+  if ((rc = hge_sched_begin(ctx, 0, num_edges, inc->e2n_ptr, num_nodes, &eh)) != HGE_OK) return fail(rc);
+  if (sharded) {
+    // the sharded edge half runs slice by slice so that the all-reduce of one slice's partial
+    // sums overlaps the gather of the next
+    inc->edge_slices.resize((size_t)num_slices);
+    inc->slice_bounds.resize((size_t)num_slices + 1);
+    for (int k = 0; k <= num_slices; ++k)
+      inc->slice_bounds[(size_t)k] = (int32_t)((int64_t)num_edges * k / num_slices);
+    for (int k = 0; k < num_slices; ++k) {
+      rc = hge_sched_begin(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
+                           inc->e2n_ptr, num_nodes, &inc->edge_slices[(size_t)k]);
+      if (rc != HGE_OK) return fail(rc);
+    }
+  }
+
+  if (mem == HGE_MEM_HOST) {
+    if (nnz_a)
+      e = cudaMemcpyAsync(inc->n2e_idx, n2e_idx, (size_t)nnz_a * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz_b)
+      e = cudaMemcpyAsync(inc->e2n_idx, e2n_idx, (size_t)nnz_b * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "column-id upload");
   }
   // edge weight sums: sum over (local) members n of 1 / deg(n); node degrees are complete
   rc = compute_wsum(ctx, num_edges, inc->e2n_ptr, inc->e2n_idx, nh.deg, &inc->edge_wsum);
@@ -1048,7 +983,7 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
 }
 
 // Second phase: edge degrees / weight sums are final (global).  Builds the inverse weight sums
-// and the gather schedules.
+// and the work items of the gather schedules.
 static int incidence_finish(hge_incidence* inc) {
   hge_ctx* ctx = inc->ctx;
   HgeHalfSchedule& nh = inc->node_half;
@@ -1059,25 +994,13 @@ static int incidence_finish(hge_incidence* inc) {
   hge_dev_free(ctx, node_wsum);
   if (rc != HGE_OK) return rc;
   HGE_TRY(invert_wsum(ctx, inc->E, inc->edge_wsum, &eh.invs));
-  HGE_TRY(build_half_schedule(ctx, 0, inc->N, inc->h_n2e_ptr, "node", &nh));
-  HGE_TRY(build_half_schedule(ctx, 0, inc->E, inc->h_e2n_ptr, "edge", &eh));
-  if (inc->sharded) {
-    // the sharded edge half runs slice by slice so that the all-reduce of one slice's partial
-    // sums overlaps the gather of the next
-    const int num_slices = inc->num_slices;
-    inc->edge_slices.resize((size_t)num_slices);
-    inc->slice_bounds.resize((size_t)num_slices + 1);
-    for (int k = 0; k <= num_slices; ++k)
-      inc->slice_bounds[(size_t)k] = (int32_t)((int64_t)inc->E * k / num_slices);
-    for (int k = 0; k < num_slices; ++k) {
-      HgeHalfSchedule& sl = inc->edge_slices[(size_t)k];
-      sl.ptr = eh.ptr;
-      sl.idx = eh.idx;
-      sl.deg = eh.deg;
-      sl.invs = eh.invs;
-      HGE_TRY(build_half_schedule(ctx, inc->slice_bounds[(size_t)k], inc->slice_bounds[(size_t)k + 1],
-                                  inc->h_e2n_ptr, "edge", &sl));
-    }
+  HGE_TRY(hge_sched_finish(ctx, "node", &nh));
+  HGE_TRY(hge_sched_finish(ctx, "edge", &eh));
+  for (HgeHalfSchedule& sl : inc->edge_slices) {
+    sl.idx = eh.idx;
+    sl.deg = eh.deg;
+    sl.invs = eh.invs;
+    HGE_TRY(hge_sched_finish(ctx, "edge", &sl));
   }
   inc->finished = true;
   return HGE_OK;
@@ -1220,8 +1143,6 @@ int hge_algdist_destroy(hge_algdist* st) {
   hge_dev_free(ctx, st->mm);
   hge_dev_free(ctx, st->partials);
   hge_dev_free(ctx, st->counters);
-  hge_dev_free(ctx, st->stage_n);
-  hge_dev_free(ctx, st->stage_e);
   delete st;
   return HGE_OK;
 }
@@ -1236,14 +1157,21 @@ int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem)
   const float* dn = xn;
   const float* de = xe;
   if (mem == HGE_MEM_HOST) {
-    if (!st->stage_n) HGE_TRY(hge_dev_alloc(ctx, &st->stage_n, (size_t)inc->N * st->R));
-    if (!st->stage_e) HGE_TRY(hge_dev_alloc(ctx, &st->stage_e, (size_t)inc->E * st->R));
-    HGE_CUDA(cudaMemcpyAsync(st->stage_n, xn, (size_t)inc->N * st->R * 4, cudaMemcpyHostToDevice,
-                             ctx->stream));
-    HGE_CUDA(cudaMemcpyAsync(st->stage_e, xe, (size_t)inc->E * st->R * 4, cudaMemcpyHostToDevice,
-                             ctx->stream));
-    dn = st->stage_n;
-    de = st->stage_e;
+    // upload on the copy stream: it starts now, next to whatever set-up work is still queued
+    // on the main stream, which only waits for it right before k_load_rows
+    float* stage = nullptr;
+    HGE_TRY(hge_ctx_stage(ctx, (size_t)(inc->N + (int64_t)inc->E) * st->R, &stage));
+    float* sn = stage;
+    float* se = stage + (size_t)inc->N * st->R;
+    HGE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_idle, 0));
+    HGE_CUDA(cudaMemcpyAsync(sn, xn, (size_t)inc->N * st->R * 4, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    HGE_CUDA(cudaMemcpyAsync(se, xe, (size_t)inc->E * st->R * 4, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    HGE_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    HGE_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    dn = sn;
+    de = se;
   }
   k_fill_minmax<<<grid_1d(ctx, (int64_t)std::max(1, st->max_iters) * 2 * st->ld, kBlock), kBlock, 0,
                   ctx->stream>>>(st->mm, std::max(1, st->max_iters), st->ld);
@@ -1254,6 +1182,7 @@ int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem)
   k_load_rows<<<grid_1d(ctx, (int64_t)inc->E * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
       inc->E, st->R, st->ld, de, inc->edge_half.deg, st->ye);
   HGE_CHECK_LAUNCH(ctx);
+  if (mem == HGE_MEM_HOST) HGE_CUDA(cudaEventRecord(ctx->stage_idle, ctx->stream));
   return HGE_OK;
 }
 
@@ -1319,10 +1248,10 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
   float* dn = xn;
   float* de = xe;
   if (mem == HGE_MEM_HOST) {
-    if (!st->stage_n) HGE_TRY(hge_dev_alloc(ctx, &st->stage_n, (size_t)inc->N * st->R));
-    if (!st->stage_e) HGE_TRY(hge_dev_alloc(ctx, &st->stage_e, (size_t)inc->E * st->R));
-    dn = st->stage_n;
-    de = st->stage_e;
+    float* stage = nullptr;
+    HGE_TRY(hge_ctx_stage(ctx, (size_t)(inc->N + (int64_t)inc->E) * st->R, &stage));
+    dn = stage;
+    de = stage + (size_t)inc->N * st->R;
   }
   k_store_rows<<<grid_1d(ctx, (int64_t)inc->N * st->R, kBlock), kBlock, 0, ctx->stream>>>(
       inc->N, st->R, st->ld, st->yn, inc->node_half.deg, mm, dn);
@@ -1333,6 +1262,7 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
   if (mem == HGE_MEM_HOST) {
     HGE_CUDA(cudaMemcpyAsync(xn, dn, (size_t)inc->N * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
     HGE_CUDA(cudaMemcpyAsync(xe, de, (size_t)inc->E * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaEventRecord(ctx->stage_idle, ctx->stream));
     HGE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return HGE_OK;
@@ -1375,3 +1305,19 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
 }
 
 }  // extern "C"
+
+// Host copy of the row pointers of one CSR (the weighting entry points cut rows into segments
+// on the host); fetched from the device on first use.
+int hge_incidence_host_ptr(hge_incidence* inc, int order, const std::vector<int64_t>** out) {
+  std::vector<int64_t>& h = order == 0 ? inc->h_n2e_ptr : inc->h_e2n_ptr;
+  const size_t n = (size_t)(order == 0 ? inc->N : inc->E) + 1;
+  if (h.size() != n) {
+    h.resize(n);
+    hge_ctx* ctx = inc->ctx;
+    HGE_CUDA(cudaMemcpyAsync(h.data(), order == 0 ? inc->n2e_ptr : inc->e2n_ptr, n * 8,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = &h;
+  return HGE_OK;
+}

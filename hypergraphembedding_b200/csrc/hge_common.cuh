@@ -52,19 +52,24 @@ struct hge_ctx {
   int blocks_per_sm;
   int use_bulk;          // long rows through the bulk-copy engine (k_heavy_bulk)
   int64_t launches;
-  // pinned staging arena (bump allocation; chunks are kept for re-use)
-  void* pinned_chunk[32];
-  size_t pinned_size[32];
-  int pinned_chunks;
-  int pinned_cur;
-  size_t pinned_off;
-  bool pinned_in_flight;
+  // ring of 64-byte pinned host slots for small device -> host read-backs (schedule statistics)
+  char* pinned_ring;
+  int pinned_next;
+  // host-buffer calls: dense staging block on the device (grow-only) and a copy stream, so the
+  // upload of the initial vectors overlaps the set-up kernels still queued on `stream`
+  float* stage;
+  size_t stage_floats;
+  cudaStream_t copy_stream;
+  cudaEvent_t copy_done;    // recorded on copy_stream after an upload into `stage`
+  cudaEvent_t stage_idle;   // recorded on `stream` after the last reader / writer of `stage`
 };
 
-// Pinned host memory that stays valid until the next hge_ctx_pinned_reset (which drains the
-// stream first if copies out of the arena may still be running).  nullptr on failure.
-void* hge_ctx_pinned(hge_ctx* ctx, size_t bytes);
-void hge_ctx_pinned_reset(hge_ctx* ctx);
+// Staging block of at least `floats` floats (contents undefined).  Growing it drains the stream.
+int hge_ctx_stage(hge_ctx* ctx, size_t floats, float** out);
+
+// One 64-byte pinned host slot; slots are handed out round-robin from a ring of 256, so a slot
+// stays untouched until 255 later requests on the same context.  nullptr on failure.
+void* hge_ctx_pinned_slot(hge_ctx* ctx);
 
 // Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the
 // context's stream; hge_ctx_create raises the pool's release threshold so freed blocks are

@@ -16,42 +16,45 @@ void hge_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void* hge_ctx_pinned(hge_ctx* ctx, size_t bytes) {
-  bytes = (bytes + 255) & ~(size_t)255;
-  ctx->pinned_in_flight = true;
-  // first chunk at or after the current one with room
-  for (int k = ctx->pinned_cur; k < ctx->pinned_chunks; ++k) {
-    const size_t off = (k == ctx->pinned_cur) ? ctx->pinned_off : 0;
-    if (off + bytes <= ctx->pinned_size[k]) {
-      ctx->pinned_cur = k;
-      ctx->pinned_off = off + bytes;
-      return static_cast<char*>(ctx->pinned_chunk[k]) + off;
+void* hge_ctx_pinned_slot(hge_ctx* ctx) {
+  if (!ctx->pinned_ring) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, 256 * 64) != cudaSuccess) {
+      cudaGetLastError();
+      hge_set_error("cudaMallocHost of the pinned slot ring failed");
+      return nullptr;
     }
+    ctx->pinned_ring = static_cast<char*>(p);
+    ctx->pinned_next = 0;
   }
-  if (ctx->pinned_chunks == 32) {
-    hge_set_error("pinned staging arena exhausted");
-    return nullptr;
-  }
-  const size_t size = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
-  void* p = nullptr;
-  if (cudaMallocHost(&p, size) != cudaSuccess) {
-    cudaGetLastError();
-    hge_set_error("cudaMallocHost of %zu bytes failed", size);
-    return nullptr;
-  }
-  const int k = ctx->pinned_chunks++;
-  ctx->pinned_chunk[k] = p;
-  ctx->pinned_size[k] = size;
-  ctx->pinned_cur = k;
-  ctx->pinned_off = bytes;
-  return p;
+  char* slot = ctx->pinned_ring + (size_t)(ctx->pinned_next & 255) * 64;
+  ctx->pinned_next++;
+  return slot;
 }
 
-void hge_ctx_pinned_reset(hge_ctx* ctx) {
-  if (ctx->pinned_in_flight) cudaStreamSynchronize(ctx->stream);
-  ctx->pinned_in_flight = false;
-  ctx->pinned_cur = 0;
-  ctx->pinned_off = 0;
+int hge_ctx_stage(hge_ctx* ctx, size_t floats, float** out) {
+  if (!ctx->copy_stream) {
+    HGE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    HGE_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    HGE_CUDA(cudaEventCreateWithFlags(&ctx->stage_idle, cudaEventDisableTiming));
+  }
+  if (ctx->stage_floats < floats) {
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+    HGE_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_floats = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->stage), floats * sizeof(float));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      hge_set_error("cudaMalloc of the %zu-byte staging block failed: %s", floats * sizeof(float),
+                    cudaGetErrorString(e));
+      return HGE_ERR_NOMEM;
+    }
+    ctx->stage_floats = floats;
+  }
+  *out = ctx->stage;
+  return HGE_OK;
 }
 
 extern "C" {
@@ -92,10 +95,13 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->use_bulk = 0;
   if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;
   ctx->launches = 0;
-  ctx->pinned_chunks = 0;
-  ctx->pinned_cur = 0;
-  ctx->pinned_off = 0;
-  ctx->pinned_in_flight = false;
+  ctx->pinned_ring = nullptr;
+  ctx->pinned_next = 0;
+  ctx->stage = nullptr;
+  ctx->stage_floats = 0;
+  ctx->copy_stream = nullptr;
+  ctx->copy_done = nullptr;
+  ctx->stage_idle = nullptr;
   // NULL selects the legacy default stream, which is also torch's default stream, so work
   // queued by the caller on that stream is ordered with ours.
   ctx->stream = reinterpret_cast<cudaStream_t>(stream);
@@ -114,7 +120,14 @@ int hge_ctx_destroy(hge_ctx* ctx) {
   if (!ctx) return HGE_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int k = 0; k < ctx->pinned_chunks; ++k) cudaFreeHost(ctx->pinned_chunk[k]);
+  if (ctx->pinned_ring) cudaFreeHost(ctx->pinned_ring);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_done);
+    cudaEventDestroy(ctx->stage_idle);
+  }
+  if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HGE_OK;

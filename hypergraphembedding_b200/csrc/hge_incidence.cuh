@@ -47,7 +47,21 @@ struct HgeHalfSchedule {
   int32_t chunk_sz = 0;
   int32_t max_deg = 0;
   int32_t first_empty = -1;       // first row without incidences, or -1
+  // transient, between hge_sched_begin and hge_sched_finish (csrc/hge_schedule.cu)
+  int32_t row0 = 0;
+  int32_t* sorted_rows = nullptr; // device: row ids by descending degree
+  long long* d_stats = nullptr;
+  long long* h_stats = nullptr;   // pinned slot
+  cudaEvent_t stats_ready = nullptr;
 };
+
+// Device-side construction of a half schedule for rows [row0, row1) of a CSR whose row pointers
+// are on the device.  begin: sort + statistics (asynchronous); finish: one event wait, then
+// the work items (needs s->invs).  release frees everything the two allocated.
+int hge_sched_begin(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* d_ptr,
+                    int64_t max_degree_possible, HgeHalfSchedule* s);
+int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s);
+void hge_sched_release(const hge_ctx* ctx, HgeHalfSchedule* s);
 
 struct hge_incidence {
   hge_ctx* ctx = nullptr;
@@ -69,6 +83,8 @@ struct hge_incidence {
   std::vector<int32_t> slice_bounds;
   hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls
 };
+
+int hge_incidence_host_ptr(hge_incidence* inc, int order, const std::vector<int64_t>** out);
 
 // Peer-memory exchange arena of one shard (csrc/hge_p2p.cu): one cudaMalloc block, exported to
 // the other ranks of the node through CUDA IPC.
@@ -100,8 +116,6 @@ struct hge_algdist {
   int32_t* mm = nullptr;        // [max_iters][2][ld]
   float4* partials = nullptr;   // max over the two halves
   int32_t* counters = nullptr;
-  float* stage_n = nullptr;     // host-call staging (dense [N, R] / [E, R])
-  float* stage_e = nullptr;
   int grid = 0;
   hge_p2p* p2p = nullptr;
 };

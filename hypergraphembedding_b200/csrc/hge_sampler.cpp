@@ -99,18 +99,8 @@ struct Mt19937 {
     return mask;
   }
 
-  // rk_interval: uniform in [0, mx]; mx == 0 consumes nothing.
-  inline uint32_t interval(uint32_t mx) {
-    if (mx == 0) return 0;
-    const uint32_t mask = mask_of(mx);
-    uint32_t v;
-    do {
-      v = next32() & mask;
-    } while (v > mx);
-    return v;
-  }
-
-  // `count` draws of interval(mx) into out[]: the raw stream is filtered without a
+  // `count` draws of rk_interval(mx) (uniform in [0, mx]; mx == 0 consumes nothing) into out[]:
+  // the raw stream is filtered without a
   // data-dependent branch (every masked output is stored, the write index only advances when
   // it is accepted); the rejection branch of the scalar form mispredicts ~25 % of the time.
   void interval_many(uint32_t mx, int64_t count, uint32_t* out) {

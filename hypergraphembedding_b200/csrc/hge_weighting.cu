@@ -440,7 +440,9 @@ int hge_incidence_l2(hge_ctx* ctx, hge_incidence* inc, const float* xn, const fl
   HGE_REQUIRE(order == 0 || order == 1, "hge_incidence_l2: order must be 0 or 1");
   HGE_CUDA(cudaSetDevice(ctx->device));
   const HgeHalfSchedule& half = order == 0 ? inc->node_half : inc->edge_half;
-  const std::vector<int64_t>& h_ptr = order == 0 ? inc->h_n2e_ptr : inc->h_e2n_ptr;
+  const std::vector<int64_t>* h_ptr_p = nullptr;
+  HGE_TRY(hge_incidence_host_ptr(inc, order, &h_ptr_p));
+  const std::vector<int64_t>& h_ptr = *h_ptr_p;
   Staged<float> s_xn, s_xe, s_out;
   HGE_TRY(s_xn.init(ctx, xn, (size_t)inc->N * R, mem, true, false));
   HGE_TRY(s_xe.init(ctx, xe, (size_t)inc->E * R, mem, true, false));

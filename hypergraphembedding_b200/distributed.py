@@ -50,6 +50,34 @@ class _CudaView(object):
                                      "data": (int(ptr), False), "version": 2}
 
 
+# Exchange arenas are expensive to set up (cudaMalloc + memset, IPC handle swap, mapping of every
+# peer, two host barriers on tear-down), so they are pooled per process and re-used by later
+# relaxations of the same shape; all ranks run the same call sequence, so they hit and miss the
+# pool together.  release_peer_arenas() is the collective tear-down.
+_ARENA_POOL = {}
+_TOPOLOGY_OK = {}
+
+
+def release_peer_arenas(dist=None, group=None):
+  """Collective: unmaps and frees every pooled exchange arena.  Call on all ranks before the
+  process group is destroyed (otherwise the memory is released at process exit)."""
+  entries = [e for e in _ARENA_POOL.values() if not e["in_use"]]
+  for key in [k for k, e in _ARENA_POOL.items() if not e["in_use"]]:
+    del _ARENA_POOL[key]
+  if not entries:
+    return
+  if dist is None:
+    import torch.distributed as dist
+  for e in entries:
+    e["ctx"].sync()
+  dist.barrier(group=group)
+  for e in entries:
+    e["arena"].close_peers()
+  dist.barrier(group=group)
+  for e in entries:
+    e["arena"].close()
+
+
 class NativeOps(object):
   """The per-rank kernels of libhge_b200.so behind the interface ShardedRelaxation drives."""
 
@@ -121,18 +149,30 @@ class NativeOps(object):
     self.state.store(sweeps_done, xn, xe)
 
   # ---- peer-memory exchange (csrc/hge_p2p.cu) ------------------------------------------
-  def enable_p2p(self, dist, group):
-    """Creates this rank's exchange arena, swaps the 64-byte IPC handles with the other ranks
-    and attaches the arena to the relaxation state."""
+  def enable_p2p(self, dist, group, pooled=True):
+    """Attaches this rank's exchange arena to the relaxation state.  A pooled arena of the same
+    shape is re-used; otherwise one is created, its 64-byte IPC handle swapped with the other
+    ranks and the peers' arenas mapped."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    self.arena = _native.PeerArena(self.ctx, rank, world, self.num_edges, self.ld)
-    mine = self.torch.from_numpy(self.arena.export()).to(self.device)
-    every = [self.torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(every, mine, group=group)
-    self.arena.open_peers(self.torch.stack(every).cpu().numpy())
+    key = (id(self.ctx), id(group), rank, world, self.num_edges, self.ld)
+    entry = _ARENA_POOL.get(key) if pooled else None
+    if entry is not None and not entry["in_use"]:
+      self.arena = entry["arena"]
+    else:
+      self.arena = _native.PeerArena(self.ctx, rank, world, self.num_edges, self.ld)
+      mine = self.torch.from_numpy(self.arena.export()).to(self.device)
+      every = [self.torch.empty_like(mine) for _ in range(world)]
+      dist.all_gather(every, mine, group=group)
+      self.arena.open_peers(self.torch.stack(every).cpu().numpy())
+      dist.barrier(group=group)
+      entry = {"arena": self.arena, "ctx": self.ctx, "in_use": False}
+      if pooled and key not in _ARENA_POOL:
+        _ARENA_POOL[key] = entry
+    entry["in_use"] = True
+    self._arena_entry = entry
+    self._arena_pooled = _ARENA_POOL.get(key) is entry
     self.state.attach_p2p(self.arena)
     self._dist, self._group = dist, group
-    dist.barrier(group=group)
 
   def sweep_p2p(self, t):
     self.state.sweep_p2p(t)
@@ -142,16 +182,24 @@ class NativeOps(object):
 
   def close(self):
     arena = getattr(self, "arena", None)
-    if arena is not None:
+    pooled = arena is not None and self._arena_pooled
+    if arena is not None and not pooled:
       # nobody may free an arena a peer still has mapped or is still writing to
       self.ctx.sync()
       self._dist.barrier(group=self._group)
       arena.close_peers()
       self._dist.barrier(group=self._group)
     if self.state is not None:
+      if pooled:
+        self.ctx.sync()        # the state's kernels may still be writing into the arena
       self.state.close()
+      self.state = None
     if arena is not None:
-      arena.close()
+      if pooled:
+        self._arena_entry["in_use"] = False
+      else:
+        arena.close()
+      self.arena = None
     self.inc.close()
 
 
@@ -183,7 +231,7 @@ class ShardedRelaxation(object):
     # per rank), "nccl" = host-interleaved NCCL / gloo collectives
     assert comm in ("auto", "p2p", "nccl")
     can_p2p = hasattr(self.ops, "enable_p2p") and dist.get_backend(group) == "nccl" and \
-        self._one_gpu_per_rank_on_one_node()
+        self._one_gpu_per_rank_on_one_node()   # cached per group
     if comm == "p2p" and not can_p2p:
       raise RuntimeError("peer-memory exchange needs NCCL ranks on distinct GPUs of one node")
     self.use_p2p = can_p2p and comm in ("auto", "p2p")
@@ -196,11 +244,15 @@ class ShardedRelaxation(object):
   def _one_gpu_per_rank_on_one_node(self):
     import socket
     torch, dist = self.torch, self.dist
+    key = (id(self.group), torch.cuda.current_device())
+    if key in _TOPOLOGY_OK:
+      return _TOPOLOGY_OK[key]
     props = torch.cuda.get_device_properties(torch.cuda.current_device())
     mine = (socket.gethostname(), str(getattr(props, "uuid", torch.cuda.current_device())))
     every = [None] * dist.get_world_size(self.group)
     dist.all_gather_object(every, mine, group=self.group)
-    return len({h for h, _ in every}) == 1 and len({u for _, u in every}) == len(every)
+    _TOPOLOGY_OK[key] = len({h for h, _ in every}) == 1 and len({u for _, u in every}) == len(every)
+    return _TOPOLOGY_OK[key]
 
   def sweep(self, t):
     if self.use_p2p:

@@ -138,10 +138,22 @@ def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, us
       relax.run(xn, xe)
       torch.cuda.synchronize()
       xn, xe = xn.cpu().numpy(), xe.cpu().numpy()
+      if relax.use_p2p:
+        # a second relaxation of the same shape re-uses the pooled exchange arena
+        relax.close()
+        relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices, comm=comm)
+        assert len(hd._ARENA_POOL) == 1
+        xn2 = torch.from_numpy(xn0[r0:r1].copy()).cuda()
+        xe2 = torch.from_numpy(xe0.copy()).cuda()
+        relax.run(xn2, xe2)
+        torch.cuda.synchronize()
+        assert np.array_equal(xn2.cpu().numpy(), xn) and np.array_equal(xe2.cpu().numpy(), xe)
     else:
       xn, xe = xn0[r0:r1].copy(), xe0.copy()
       relax.run(xn, xe)
     relax.close()
+    hd.release_peer_arenas(dist)
+    assert not hd._ARENA_POOL
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), xn=xn, xe=xe, r0=r0, r1=r1)
   finally:
     dist.destroy_process_group()
