@@ -107,6 +107,21 @@ SIGNATURES = {
                                            c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp,
                                            ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "hge_sampler_set_threads": (ctypes.c_int, [ctypes.c_int]),
+    "hge_hypergraph_parse": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "hge_hypergraph_destroy": (ctypes.c_int, [c_vp]),
+    "hge_hypergraph_sizes": (ctypes.c_int, [c_vp, c_vp]),
+    "hge_hypergraph_arrays": (ctypes.c_int, [c_vp] * 9),
+    "hge_hypergraph_compress": (ctypes.c_int, [c_vp] * 8),
+    "hge_embedding_wire_size": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
+                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p,
+                                               ctypes.POINTER(ctypes.c_size_t)]),
+    "hge_embedding_write": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int64, c_vp,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, c_vp,
+                                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "hge_embedding_parse": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "hge_embedding_destroy": (ctypes.c_int, [c_vp]),
+    "hge_embedding_sizes": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "hge_embedding_arrays": (ctypes.c_int, [c_vp] * 7),
     "hge_sample_neighbors": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64,
                                             ctypes.c_int, c_vp, c_vp, c_vp]),
 }

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _native
 from .hypergraph_pb2 import HypergraphEmbedding
-from .hypergraph_util import compressed_incidence, csr_arrays
+from .hypergraph_util import HypergraphArrays, csr_arrays, embedding_to_wire
 
 log = logging.getLogger()
 
@@ -45,7 +45,13 @@ def EmbedAlgebraicDistance(hypergraph,
   """algebraic_distance.py:126-175.  ``run_in_parallel`` / ``disable_pbar`` are accepted for
   compatibility; the work is one GPU call either way."""
   del run_in_parallel, disable_pbar
-  node_ids, edge_ids, node2edges = compressed_incidence(hypergraph)
+  # proto -> arrays through the wire format (csrc/hge_proto.cpp): CompressRange, ToCsrMatrix and
+  # the transpose without a Python loop over incidences
+  arrays = HypergraphArrays(hypergraph)
+  try:
+    node_ids, edge_ids, a_ptr, a_idx, b_ptr, b_idx = arrays.compress()
+  finally:
+    arrays.close()
   num_nodes = len(node_ids)   # == max(compressed ids) + 1, algebraic_distance.py:135-136
   num_edges = len(edge_ids)
 
@@ -55,18 +61,16 @@ def EmbedAlgebraicDistance(hypergraph,
   edge_embeddings = np.random.random((num_edges, dimension)).astype(np.float32)
 
   log.info("Uploading node-edge incidence")
-  incidence = make_incidence(node2edges)
+  incidence = _native.Incidence(_native.default_context(), num_nodes, num_edges, a_ptr, a_idx,
+                                b_ptr, b_idx)
   try:
     log.info("Performing iterations of Algebraic Distance Calculations")
     relax(incidence, node_embeddings, edge_embeddings, iterations)
   finally:
     incidence.close()
 
+  # arrays -> proto through the wire format: no per-row packing loop (algebraic_distance.py:169-174)
   embedding = HypergraphEmbedding()
-  embedding.dim = dimension
-  embedding.method_name = "AlgebraicDistance"
-  for idx, node_id in enumerate(node_ids.tolist()):
-    embedding.node[node_id].values.extend(node_embeddings[idx, :].tolist())
-  for idx, edge_id in enumerate(edge_ids.tolist()):
-    embedding.edge[edge_id].values.extend(edge_embeddings[idx, :].tolist())
+  embedding.ParseFromString(embedding_to_wire(node_ids, node_embeddings, edge_ids, edge_embeddings,
+                                              dimension, "AlgebraicDistance"))
   return embedding

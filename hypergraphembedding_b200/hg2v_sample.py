@@ -238,21 +238,26 @@ def _pad(indptr, rows):
 
 
 def embedding_to_arrays(embedding, num_nodes, num_edges):
-  """Dense fp32 [num_nodes, R] / [num_edges, R] from a HypergraphEmbedding proto."""
-  dim = None
-  for vec in embedding.node.values():
-    dim = len(vec.values)
-    break
-  assert dim is not None and dim > 0, "embedding has no node vectors"
-  xn = np.zeros((num_nodes, dim), dtype=np.float32)
-  xe = np.zeros((num_edges, dim), dtype=np.float32)
-  for idx, vec in embedding.node.items():
-    if 0 <= idx < num_nodes:
-      xn[idx] = vec.values
-  for idx, vec in embedding.edge.items():
-    if 0 <= idx < num_edges:
-      xe[idx] = vec.values
-  return xn, xe
+  """Dense fp32 [num_nodes, R] / [num_edges, R] from a HypergraphEmbedding proto (rows of ids
+  without a vector stay zero), read from the serialized message (csrc/hge_proto.cpp)."""
+  from .hypergraph_util import embedding_from_wire
+  ids_n, ptr_n, val_n, ids_e, ptr_e, val_e, _ = embedding_from_wire(embedding)
+  assert len(ids_n) > 0 and ptr_n[-1] > 0, "embedding has no node vectors"
+
+  def dense(ids, ptr, vals, rows, dim):
+    out = np.zeros((rows, dim), dtype=np.float32)
+    lens = np.diff(ptr)
+    keep = (ids >= 0) & (ids < rows)
+    assert np.all(lens[keep] == dim), "embedding vectors have different lengths"
+    if np.all(lens == dim):
+      out[ids[keep]] = vals.reshape(-1, dim)[keep]
+    else:
+      for i in np.nonzero(keep)[0]:
+        out[ids[i]] = vals[ptr[i]:ptr[i + 1]]
+    return out
+
+  dim = int(np.diff(ptr_n).max())
+  return dense(ids_n, ptr_n, val_n, num_nodes, dim), dense(ids_e, ptr_e, val_e, num_edges, dim)
 
 
 ################################################################################

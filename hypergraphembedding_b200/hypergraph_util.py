@@ -5,11 +5,13 @@ Mirrors the part of the reference's ``hypergraph_util.py`` that the path calls
 ``CompressRange``:223), with the same names, arguments and results, and adds the array
 forms the CUDA kernels consume (int64 row pointers + int32 sorted column ids).
 """
+import ctypes
 import logging
 
 import numpy as np
 import scipy.sparse as sps
 
+from . import _native
 from .hypergraph_pb2 import Hypergraph
 
 log = logging.getLogger()
@@ -53,14 +55,14 @@ def _coo_to_csr(rows, cols, shape=None):
 
 def ToCsrMatrix(hypergraph):
   """hypergraph_util.py:96-114: N x E bool CSR from ``node.edges``; shape = max id + 1;
-  duplicates collapse; column ids sorted."""
+  duplicates collapse; column ids sorted.  The incidences are read from the serialized
+  message (csrc/hge_proto.cpp), not by a Python loop over them."""
   if IsEmpty(hypergraph):
     return sps.csr_matrix([])
-  rows, cols = [], []
-  for node_idx, node in hypergraph.node.items():
-    edges = node.edges
-    rows.extend([node_idx] * len(edges))
-    cols.extend(edges)
+  arrays = HypergraphArrays(hypergraph)
+  rows = np.repeat(arrays.node_ids, np.diff(arrays.node_ptr))
+  cols = arrays.node_edges
+  arrays.close()
   m = _coo_to_csr(rows, cols)
   m.sum_duplicates()
   return m
@@ -70,11 +72,10 @@ def ToEdgeCsrMatrix(hypergraph):
   """hypergraph_util.py:117-135: E x N bool CSR from ``edge.nodes``."""
   if IsEmpty(hypergraph):
     return sps.csr_matrix([])
-  rows, cols = [], []
-  for edge_idx, edge in hypergraph.edge.items():
-    nodes = edge.nodes
-    rows.extend([edge_idx] * len(nodes))
-    cols.extend(nodes)
+  arrays = HypergraphArrays(hypergraph)
+  rows = np.repeat(arrays.edge_ids, np.diff(arrays.edge_ptr))
+  cols = arrays.edge_nodes
+  arrays.close()
   m = _coo_to_csr(rows, cols)
   m.sum_duplicates()
   return m
@@ -187,3 +188,120 @@ def compressed_incidence(hypergraph):
   a = _coo_to_csr(r, c, shape=(len(node_ids), len(edge_ids)))
   a.sum_duplicates()
   return node_ids, edge_ids, a
+
+
+# ---------------------------------------------------------------------------------------
+# wire-format fast path (csrc/hge_proto.cpp): serialized proto <-> arrays without a Python
+# loop over incidences or rows
+# ---------------------------------------------------------------------------------------
+
+
+def _wire_bytes(message_or_bytes):
+  if isinstance(message_or_bytes, (bytes, bytearray, memoryview)):
+    return bytes(message_or_bytes)
+  return message_or_bytes.SerializeToString()
+
+
+class HypergraphArrays(object):
+  """A serialized ``Hypergraph`` read into arrays.  Per side: ids in wire order (whatever order
+  the producer's serializer emitted its map in -- not necessarily the order Python iterates the
+  map; take ``list(hypergraph.node)`` where that order matters), int64 row pointers, members in stored order (duplicates kept, as
+  in the proto), fp32 weights (default 1)."""
+
+  def __init__(self, message_or_bytes):
+    lib = _native.load_library()
+    data = _wire_bytes(message_or_bytes)
+    handle = _native.c_vp()
+    _native.check(lib.hge_hypergraph_parse(data, len(data), ctypes.byref(handle)),
+                  "hge_hypergraph_parse")
+    self._lib, self._handle = lib, handle
+    sizes = np.zeros(4, dtype=np.int64)
+    _native.check(lib.hge_hypergraph_sizes(handle, _native.ptr(sizes)))
+    self.num_node_entries, self.num_edge_entries, n_members, e_members = (int(v) for v in sizes)
+    self.node_ids = np.empty(self.num_node_entries, np.int32)
+    self.node_ptr = np.empty(self.num_node_entries + 1, np.int64)
+    self.node_edges = np.empty(n_members, np.int32)
+    self.node_weight = np.empty(self.num_node_entries, np.float32)
+    self.edge_ids = np.empty(self.num_edge_entries, np.int32)
+    self.edge_ptr = np.empty(self.num_edge_entries + 1, np.int64)
+    self.edge_nodes = np.empty(e_members, np.int32)
+    self.edge_weight = np.empty(self.num_edge_entries, np.float32)
+    _native.check(lib.hge_hypergraph_arrays(
+        handle, *[_native.ptr(a) for a in (self.node_ids, self.node_ptr, self.node_edges,
+                                           self.node_weight, self.edge_ids, self.edge_ptr,
+                                           self.edge_nodes, self.edge_weight)]))
+
+  def compress(self):
+    """CompressRange + ToCsrMatrix + transpose (algebraic_distance.py:133-146) on the arrays:
+    (sorted node ids, sorted edge ids, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx).  Raises
+    AssertionError when a node lists an edge that is not a key of the edge map (Relabel
+    asserts the same, hypergraph_util.py:207)."""
+    n, e = self.num_node_entries, self.num_edge_entries
+    cap = max(1, len(self.node_edges))
+    node_ids, edge_ids = np.empty(n, np.int32), np.empty(e, np.int32)
+    a_ptr, a_idx = np.empty(n + 1, np.int64), np.empty(cap, np.int32)
+    b_ptr, b_idx = np.empty(e + 1, np.int64), np.empty(cap, np.int32)
+    nnz = ctypes.c_int64(0)
+    _native.check(self._lib.hge_hypergraph_compress(
+        self._handle, _native.ptr(node_ids), _native.ptr(edge_ids), _native.ptr(a_ptr),
+        _native.ptr(a_idx), _native.ptr(b_ptr), _native.ptr(b_idx), ctypes.byref(nnz)),
+                  "hge_hypergraph_compress")
+    return node_ids, edge_ids, a_ptr, a_idx[:nnz.value], b_ptr, b_idx[:nnz.value]
+
+  def close(self):
+    if getattr(self, "_handle", None):
+      self._lib.hge_hypergraph_destroy(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+def embedding_to_wire(node_ids, node_vectors, edge_ids, edge_vectors, dim, method_name):
+  """Serialized ``HypergraphEmbedding`` from dense fp32 rows keyed by strictly ascending ids:
+  field for field what the protobuf runtime emits for the reference's message (map entries in
+  ascending key order)."""
+  lib = _native.load_library()
+  node_ids = np.ascontiguousarray(node_ids, dtype=np.int32)
+  edge_ids = np.ascontiguousarray(edge_ids, dtype=np.int32)
+  xn = np.ascontiguousarray(node_vectors, dtype=np.float32)
+  xe = np.ascontiguousarray(edge_vectors, dtype=np.float32)
+  R = int(xn.shape[1]) if xn.ndim == 2 else 0
+  assert xn.shape == (len(node_ids), R) and xe.shape == (len(edge_ids), R)
+  name = method_name.encode("utf-8") if method_name is not None else None
+  size = ctypes.c_size_t(0)
+  _native.check(lib.hge_embedding_wire_size(_native.ptr(node_ids), len(node_ids),
+                                            _native.ptr(edge_ids), len(edge_ids), R, int(dim), name,
+                                            ctypes.byref(size)), "hge_embedding_wire_size")
+  out = np.empty(size.value, dtype=np.uint8)
+  written = ctypes.c_size_t(0)
+  _native.check(lib.hge_embedding_write(_native.ptr(node_ids), len(node_ids), _native.ptr(xn),
+                                        _native.ptr(edge_ids), len(edge_ids), _native.ptr(xe), R,
+                                        int(dim), name, _native.ptr(out), out.size,
+                                        ctypes.byref(written)), "hge_embedding_write")
+  assert written.value == size.value
+  return out.tobytes()
+
+
+def embedding_from_wire(message_or_bytes):
+  """A serialized ``HypergraphEmbedding`` as (node_ids, node_ptr, node_values, edge_ids, edge_ptr,
+  edge_values, dim): ids in wire order, row pointers into the flat fp32 value arrays, dim = None
+  when the field is absent."""
+  lib = _native.load_library()
+  data = _wire_bytes(message_or_bytes)
+  handle = _native.c_vp()
+  _native.check(lib.hge_embedding_parse(data, len(data), ctypes.byref(handle)), "hge_embedding_parse")
+  try:
+    sizes = np.zeros(4, dtype=np.int64)
+    dim = ctypes.c_int32(0)
+    _native.check(lib.hge_embedding_sizes(handle, _native.ptr(sizes), ctypes.byref(dim)))
+    n, e, nv, ev = (int(v) for v in sizes)
+    out = (np.empty(n, np.int32), np.empty(n + 1, np.int64), np.empty(nv, np.float32),
+           np.empty(e, np.int32), np.empty(e + 1, np.int64), np.empty(ev, np.float32))
+    _native.check(lib.hge_embedding_arrays(handle, *[_native.ptr(a) for a in out]))
+  finally:
+    lib.hge_embedding_destroy(handle)
+  return out + (None if dim.value < 0 else int(dim.value),)

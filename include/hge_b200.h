@@ -249,6 +249,55 @@ int hge_sample_neighbors(const int64_t* n2e_ptr, const int32_t* n2e_idx, const i
                          int64_t num_samples, int k, uint32_t* state625, int32_t* out_nbr_edges,
                          int32_t* out_nbr_nodes);
 
+/* ---- hypergraph.proto wire format (host code; all pointers are host pointers) --------------
+ * The data formats either side of the path: a serialized Hypergraph (hypergraph.proto:6-23) is
+ * read straight into arrays, replacing the per-incidence Python loops of ToCsrMatrix /
+ * ToEdgeCsrMatrix (hypergraph_util.py:96-135) and CompressRange / Relabel (:198-244); the result
+ * of EmbedAlgebraicDistance is written as a serialized HypergraphEmbedding (:26-35), replacing
+ * the per-row packing loop (algebraic_distance.py:169-174).  Map entries are reported in wire
+ * order (the producing serializer's order, which need not be its map iteration order);
+ * duplicate keys: the last entry wins. */
+typedef struct hge_hypergraph hge_hypergraph;
+typedef struct hge_embedding hge_embedding;
+
+int hge_hypergraph_parse(const void* buf, size_t len, hge_hypergraph** out);
+int hge_hypergraph_destroy(hge_hypergraph* hg);
+/* sizes4 = { node entries, edge entries, sum len(node.edges), sum len(edge.nodes) } */
+int hge_hypergraph_sizes(const hge_hypergraph* hg, int64_t* sizes4);
+/* Per side: ids [entries], row pointers [entries + 1], members in stored order (duplicates
+ * kept), weights (default 1).  Any output may be NULL. */
+int hge_hypergraph_arrays(const hge_hypergraph* hg, int32_t* node_ids, int64_t* node_ptr,
+                          int32_t* node_edges, float* node_weight, int32_t* edge_ids,
+                          int64_t* edge_ptr, int32_t* edge_nodes, float* edge_weight);
+/* CompressRange + ToCsrMatrix + transpose in one pass (algebraic_distance.py:133-146): ids are
+ * replaced by their rank among the sorted keys, connections come from node.edges only, column
+ * ids are sorted and duplicates collapse.  sorted_*_ids are the inverse maps.  n2e_idx / e2n_idx
+ * need room for sum len(node.edges) entries; *nnz_out is the number stored.  An edge id that is
+ * not a key of the edge map is HGE_ERR_INVALID (Relabel asserts, hypergraph_util.py:207). */
+int hge_hypergraph_compress(const hge_hypergraph* hg, int32_t* sorted_node_ids,
+                            int32_t* sorted_edge_ids, int64_t* n2e_ptr, int32_t* n2e_idx,
+                            int64_t* e2n_ptr, int32_t* e2n_idx, int64_t* nnz_out);
+
+/* Serialized HypergraphEmbedding from dense fp32 [num_nodes, R] / [num_edges, R] rows keyed by
+ * strictly ascending ids, plus dim and method_name (NULL: absent): field for field the bytes
+ * the protobuf runtime emits for the message the reference builds (proto2: floats unpacked),
+ * with the map entries in ascending key order. */
+int hge_embedding_wire_size(const int32_t* node_ids, int64_t num_nodes, const int32_t* edge_ids,
+                            int64_t num_edges, int32_t R, int32_t dim, const char* method_name,
+                            size_t* out);
+int hge_embedding_write(const int32_t* node_ids, int64_t num_nodes, const float* xn,
+                        const int32_t* edge_ids, int64_t num_edges, const float* xe, int32_t R,
+                        int32_t dim, const char* method_name, void* out, size_t capacity,
+                        size_t* written);
+/* The reverse (input of AlgebraicDistanceSamples / WeightByDistance): ids in wire order, row
+ * pointers into the value arrays (rows may be ragged), *dim = -1 when the field is absent. */
+int hge_embedding_parse(const void* buf, size_t len, hge_embedding** out);
+int hge_embedding_destroy(hge_embedding* emb);
+int hge_embedding_sizes(const hge_embedding* emb, int64_t* sizes4, int32_t* dim);
+int hge_embedding_arrays(const hge_embedding* emb, int32_t* node_ids, int64_t* node_ptr,
+                         float* node_values, int32_t* edge_ids, int64_t* edge_ptr,
+                         float* edge_values);
+
 #ifdef __cplusplus
 }
 #endif
