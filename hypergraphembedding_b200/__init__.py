@@ -10,8 +10,9 @@ from .hypergraph_pb2 import (EvaluationMetrics, ExperimentalResult, Hypergraph,
 from .hypergraph_util import (AddNodeToEdge, CompressRange, IsEmpty, Relabel, ToCsrMatrix,
                               ToEdgeCsrMatrix)
 from .algebraic_distance import EmbedAlgebraicDistance
-from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, SampleColumns,
-                          SamplesToModelInput, SimilarityRecord)
+from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, BooleanSamplesCsr,
+                          SampleColumns, SamplesToModelInput, SimilarityRecord,
+                          SparseWeightedJaccard, WeightedJaccardSamples)
 from .hg2v_weighting import (AlphaScaleValues, ComputeSpans, DictToSparseRow, OneMinusValues,
                              UniformWeight, WeightByAlgebraicSpan, WeightByDistance,
                              WeightByDistanceCluster, WeightByNeighborhood,
@@ -21,8 +22,8 @@ __all__ = [
     "Hypergraph", "HypergraphEmbedding", "EvaluationMetrics", "ExperimentalResult",
     "AddNodeToEdge", "CompressRange", "IsEmpty", "Relabel", "ToCsrMatrix", "ToEdgeCsrMatrix",
     "EmbedAlgebraicDistance",
-    "AlgebraicDistanceSamples", "BooleanSamples", "SampleColumns", "SamplesToModelInput",
-    "SimilarityRecord",
+    "AlgebraicDistanceSamples", "BooleanSamples", "BooleanSamplesCsr", "SampleColumns",
+    "SamplesToModelInput", "SimilarityRecord", "SparseWeightedJaccard", "WeightedJaccardSamples",
     "AlphaScaleValues", "ComputeSpans", "DictToSparseRow", "OneMinusValues", "UniformWeight",
     "WeightByAlgebraicSpan", "WeightByDistance", "WeightByDistanceCluster", "WeightByNeighborhood",
     "WeightBySameTypeDistance", "ZeroOneScaleValues",

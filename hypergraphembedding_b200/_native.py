@@ -97,6 +97,12 @@ SIGNATURES = {
                                           ctypes.c_int64, c_vp, ctypes.c_int]),
     "hge_diff_type_prob": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp,
                                           ctypes.c_int]),
+    "hge_jaccard_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, c_vp,
+                                        c_vp, ctypes.c_int64, c_vp, ctypes.c_int]),
+    "hge_jaccard_centroid": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64,
+                                            c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp,
+                                            c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp,
+                                            ctypes.c_int64, c_vp, ctypes.c_int]),
     "hge_mt19937_random_raw": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp]),
     "hge_mt19937_interval": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_int64, c_vp]),
     "hge_spgemm_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -478,6 +484,49 @@ def diff_type_prob(ctx, inc, w_e2n, pn, pe):
   check(ctx.lib.hge_diff_type_prob(ctx.handle, inc.handle, ptr(w_e2n), ptr(pn), ptr(pe),
                                    int(pn.shape[0]), ptr(out), _mem(w_e2n, pn, pe)),
         "hge_diff_type_prob")
+  return out
+
+
+class FeatureCsr(object):
+  """(int64 ptr, int32 sorted idx, fp32 val, shape) of a scipy sparse feature matrix, host."""
+
+  def __init__(self, matrix):
+    import scipy.sparse as sps
+    m = sps.csr_matrix(matrix, dtype=np.float32)
+    if not m.has_canonical_format:
+      m = m.copy()
+      m.sum_duplicates()
+    self.shape = m.shape
+    self.ptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    self.idx = np.ascontiguousarray(m.indices, dtype=np.int32)
+    self.val = np.ascontiguousarray(m.data, dtype=np.float32)
+
+
+def jaccard_rows(ctx, feat, pi, pj):
+  """J(F[pi], F[pj]) for host index arrays; returns a numpy fp32 array."""
+  pi, pj = _as_i32(pi), _as_i32(pj)
+  out = np.empty(len(pi), dtype=np.float32)
+  check(ctx.lib.hge_jaccard_rows(ctx.handle, ptr(feat.ptr), ptr(feat.idx), ptr(feat.val),
+                                 feat.shape[0], len(feat.idx), ptr(pi), ptr(pj), len(pi), ptr(out),
+                                 MEM_HOST), "hge_jaccard_rows")
+  return out
+
+
+def jaccard_centroid(ctx, x, groups, feat, px, pg):
+  """J(X[px], mean of the rows F[t], t in G[pg]) for host arrays; `groups` is a CsrArrays."""
+  px, pg = _as_i32(px), _as_i32(pg)
+  assert x.shape[1] == feat.shape[1]
+  assert groups.shape[1] == feat.shape[0]
+  out = np.empty(len(px), dtype=np.float32)
+  if x is feat:
+    xa = (feat.ptr, feat.idx, feat.val)
+  else:
+    xa = (x.ptr, x.idx, x.val)
+  check(ctx.lib.hge_jaccard_centroid(
+      ctx.handle, ptr(xa[0]), ptr(xa[1]), ptr(xa[2]), x.shape[0], len(xa[1]), ptr(groups.ptr),
+      ptr(groups.idx), groups.shape[0], len(groups.idx), ptr(feat.ptr), ptr(feat.idx), ptr(feat.val),
+      feat.shape[0], len(feat.idx), ptr(px), ptr(pg), len(px), ptr(out), MEM_HOST),
+        "hge_jaccard_centroid")
   return out
 
 

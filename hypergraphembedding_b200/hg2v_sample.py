@@ -52,7 +52,7 @@ class SampleColumns(collections.abc.Sequence):
   probability, ``has_neighbors`` False a record without neighbour arrays."""
 
   FIELDS = ("left_node", "left_edge", "right_node", "right_edge", "neigh_node", "neigh_edge",
-            "nn_prob", "ee_prob", "ne_prob", "has_neighbors")
+            "nn_prob", "ee_prob", "ne_prob", "has_neighbors", "left_weight", "right_weight")
 
   def __init__(self, num_neighbors, **cols):
     self.num_neighbors = int(num_neighbors)
@@ -62,7 +62,7 @@ class SampleColumns(collections.abc.Sequence):
   @classmethod
   def build(cls, num_neighbors, count, left_node=None, left_edge=None, right_node=None,
             right_edge=None, neigh_node=None, neigh_edge=None, nn_prob=None, ee_prob=None,
-            ne_prob=None):
+            ne_prob=None, left_weight=None, right_weight=None):
     # absent columns are constant read-only views (no memory): a chunk of a streamed 1e9-record
     # result only pays for the columns it has; concatenate() materialises them
     def idx(a):
@@ -81,7 +81,8 @@ class SampleColumns(collections.abc.Sequence):
                neigh_node=np.asarray(neigh_node, np.int32).reshape(count, k) if has else none,
                neigh_edge=np.asarray(neigh_edge, np.int32).reshape(count, k) if has else none,
                nn_prob=prob(nn_prob), ee_prob=prob(ee_prob), ne_prob=prob(ne_prob),
-               has_neighbors=np.broadcast_to(np.bool_(has), (count,)))
+               has_neighbors=np.broadcast_to(np.bool_(has), (count,)),
+               left_weight=prob(left_weight), right_weight=prob(right_weight))
 
   @classmethod
   def concatenate(cls, parts):
@@ -107,6 +108,7 @@ class SampleColumns(collections.abc.Sequence):
     return SimilarityRecord(
         left_node_idx=idx(self.left_node[i]), left_edge_idx=idx(self.left_edge[i]),
         right_node_idx=idx(self.right_node[i]), right_edge_idx=idx(self.right_edge[i]),
+        left_weight=prob(self.left_weight[i]), right_weight=prob(self.right_weight[i]),
         neighbor_node_indices=self.neigh_node[i] if has else None,
         neighbor_edge_indices=self.neigh_edge[i] if has else None,
         node_node_prob=prob(self.nn_prob[i]), edge_edge_prob=prob(self.ee_prob[i]),
@@ -388,6 +390,114 @@ def BooleanSamplesCsr(incidence, num_neighbors, num_samples, neg_samples=0, node
 
 
 ################################################################################
+# WeightedJaccard Samples - helper and sampler                                 #
+################################################################################
+
+
+def SparseWeightedJaccard(row_i, row_j):
+  """hg2v_sample.py:250-275: sum of minima over sum of maxima of two sparse 1 x F rows (0 when
+  the denominator is 0)."""
+  assert row_i.shape[0] == 1
+  assert row_j.shape[0] == 1
+  assert row_i.shape[1] == row_j.shape[1]
+  feat = _native.FeatureCsr(sps.vstack([sps.csr_matrix(row_i), sps.csr_matrix(row_j)]))
+  return _native.jaccard_rows(_native.default_context(), feat, [0], [1])[0]
+
+
+def CentroidFromRows(idx, idx2targets=None, targets2features=None):
+  """hg2v_sample.py:284-299: mean of the feature rows of idx's targets as (vals, (rows, cols)).
+  Host bookkeeping kept for API compatibility; the sampler itself never materialises centroids
+  (csrc/hge_jaccard.cu evaluates them on the fly)."""
+  assert idx2targets is not None and targets2features is not None
+  rows = sps.csr_matrix(idx2targets)[idx].nonzero()[1]
+  centroid = sps.csr_matrix(targets2features)[rows].sum(axis=0) / len(rows)
+  cols = centroid.nonzero()[1]
+  return ([centroid[0, c] for c in cols], ([idx] * len(cols), list(cols)))
+
+
+def GetAllCentroids(important_indices, idx2targets, targets2features, disable_pbar):
+  """hg2v_sample.py:302-320."""
+  del disable_pbar
+  rows, cols, vals = [], [], []
+  for idx in important_indices:
+    v, (r, c) = CentroidFromRows(idx, idx2targets, targets2features)
+    vals.extend(v)
+    rows.extend(r)
+    cols.extend(c)
+  return sps.csr_matrix((vals, (rows, cols)),
+                        shape=(idx2targets.shape[0], targets2features.shape[1]))
+
+
+def SameTypeJaccardSample(indices, idx2features=None, is_edge=None):
+  """hg2v_sample.py:323-340 with explicit arguments."""
+  assert idx2features is not None
+  idx, neighbor_idx = indices
+  m = sps.csr_matrix(idx2features)
+  prob = SparseWeightedJaccard(m[idx], m[neighbor_idx])
+  if is_edge:
+    return SimilarityRecord(left_edge_idx=idx, right_edge_idx=neighbor_idx,
+                            edge_edge_prob=_alpha_scale(prob))
+  return SimilarityRecord(left_node_idx=idx, right_node_idx=neighbor_idx,
+                          node_node_prob=_alpha_scale(prob))
+
+
+def WeightedJaccardSamples(hypergraph, node2features, edge2features, num_neighbors, num_samples,
+                           run_in_parallel=True, disable_pbar=False):
+  """hg2v_sample.py:398-510: node-node / edge-edge samples weighted by the sparse weighted
+  Jaccard of their feature rows, node-edge samples by the product of J(node features, centroid
+  of the edge's members' features) and J(edge features, centroid of the node's edges'
+  features), both factors recorded as left / right weight.
+
+  Pair sets come from the global RNG exactly as the reference draws them; the neighbour arrays
+  are drawn the way the reference's single worker (``run_in_parallel=False``) draws them, from
+  a copy of the RNG state the parent had when the pair sampling ended."""
+  del run_in_parallel, disable_pbar
+  log.info("Performing input checks")
+  assert num_neighbors >= 0
+  assert num_samples >= 0
+  node_samples = [int(node.weight * num_samples) for _, node in hypergraph.node.items()]
+  edge_samples = [int(edge.weight * num_samples) for _, edge in hypergraph.edge.items()]
+
+  g = _Graph(hypergraph)
+  k = num_neighbors
+  log.info("Checking that feature matrices agree with the sparse matrices")
+  assert g.num_nodes == node2features.shape[0]     # hg2v_sample.py:430
+  assert g.num_edges == edge2features.shape[0]     # hg2v_sample.py:458
+  nf = _native.FeatureCsr(node2features)
+  ef = _native.FeatureCsr(edge2features)
+  ctx = _native.default_context()
+  state = _native.LegacyRngState()
+  parts = []
+
+  log.info("Getting node-node samples")
+  r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, node_samples, state)
+  log.info("Sampling node-node probabilities")
+  parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c,
+                                   nn_prob=_native.jaccard_rows(ctx, nf, r, c)))
+  log.info("Getting edge-edge samples")
+  r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, edge_samples, state)
+  log.info("Sampling edge-edge probabilities")
+  parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c,
+                                   ee_prob=_native.jaccard_rows(ctx, ef, r, c)))
+  log.info("Getting node-edge samples")
+  n1, e1 = _native.sample_adj_rows((g.a, g.at, g.a), g.node_rows, node_samples, state)
+  log.info("Getting edge-node samples")
+  e2, n2 = _native.sample_adj_rows((g.b, g.bt, g.b), g.edge_rows, edge_samples, state)
+  state.commit()   # the parent's stream ends here (the worker draws from a copy)
+  nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
+  nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state.copy())
+  log.info("Getting node-edge relationships")
+  # centroid of an edge = mean of its member nodes' feature rows, and vice versa
+  prob_by_node = _native.jaccard_centroid(ctx, nf, g.b, nf, nodes, edges)
+  prob_by_edge = _native.jaccard_centroid(ctx, ef, g.a, ef, edges, nodes)
+  parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
+                                   neigh_node=nbr_n, neigh_edge=nbr_e,
+                                   left_weight=prob_by_node, right_weight=prob_by_edge,
+                                   ne_prob=prob_by_node * prob_by_edge))
+  return SampleColumns.concatenate(parts)
+
+
+################################################################################
 # AlgebraicDistanceSamples - With helpers                                      #
 ################################################################################
 
@@ -534,7 +644,7 @@ def _columns_to_model_input(cols, num_neighbors, weighted):
 
   features = [inc(cols.left_node), inc(cols.left_edge), inc(cols.right_node), inc(cols.right_edge)]
   if weighted:
-    features += [zeros_f.copy(), zeros_f.copy()]
+    features += [np.nan_to_num(cols.left_weight, nan=0.0), np.nan_to_num(cols.right_weight, nan=0.0)]
   features += neigh(cols.neigh_node)
   if weighted:
     features += [zeros_f.copy() for _ in range(num_neighbors)]

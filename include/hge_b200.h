@@ -202,6 +202,26 @@ int hge_same_type_prob(hge_ctx* ctx, hge_incidence* inc, int side, const float* 
 int hge_diff_type_prob(hge_ctx* ctx, hge_incidence* inc, const float* w_e2n, const int32_t* pn,
                        const int32_t* pe, int64_t num_pairs, float* prob, int mem);
 
+/* ---- sparse weighted Jaccard (WeightedJaccardSamples, hg2v_sample.py:250-510) -----------
+ * Feature matrices are CSR with int64 row pointers, sorted int32 column ids and fp32 values
+ * >= 0 (negative values: HGE_ERR_UNSUPPORTED).  J(x, y) = sum min / sum max over the union of
+ * the non-zeros, 0 when the denominator is 0 (SparseWeightedJaccard, :250-275). */
+
+/* out[p] = J(F[pi[p]], F[pj[p]]): SameTypeJaccardSample (:323-340). */
+int hge_jaccard_rows(hge_ctx* ctx, const int64_t* ptr, const int32_t* idx, const float* val,
+                     int64_t rows, int64_t nnz, const int32_t* pi, const int32_t* pj,
+                     int64_t num_pairs, float* out, int mem);
+
+/* out[p] = J(X[px[p]], mean_{t in G[pg[p]]} F[t]): one factor of DiffTypeJaccardSample
+ * (:343-392) without materialising the centroids of CentroidFromRows / GetAllCentroids
+ * (:284-320).  G is a boolean CSR (group -> member rows of F); X and F have the same number of
+ * columns (X may be F itself).  An empty group gives 0. */
+int hge_jaccard_centroid(hge_ctx* ctx, const int64_t* xptr, const int32_t* xidx, const float* xval,
+                         int64_t xrows, int64_t xnnz, const int64_t* gptr, const int32_t* gidx,
+                         int64_t grows, int64_t gnnz, const int64_t* fptr, const int32_t* fidx,
+                         const float* fval, int64_t frows, int64_t fnnz, const int32_t* px,
+                         const int32_t* pg, int64_t num_pairs, float* out, int mem);
+
 /* ---- candidate rows and bit-exact sampling (host code; all pointers are host pointers) ---
  * The reference draws every sample from numpy's process-global legacy MT19937, sequentially
  * and with data-dependent rejection, so this part of the path runs on the host; the drawn

@@ -205,6 +205,39 @@ def gen_hobe(ref, name, hg, xn, xe, k, num_samples, seed, parallel, stride):
   save("hobe_" + name, **out)
 
 
+def gen_jaccard(ref, name, hg, feature_kind, k, num_samples, seed, xn=None, xe=None):
+  """WeightedJaccardSamples (hg2v_sample.py:398-510) with run_in_parallel=False (one worker:
+  deterministic neighbour draws from a copy of the parent's RNG state)."""
+  hc = compressed(ref, hg)
+  W = ref.hg2v_weighting
+  if feature_kind == "uniform":                    # EmbedHg2vAdjJaccard, embedding.py:339-347
+    n2f, e2f = W.UniformWeight(hc)
+  elif feature_kind == "neighborhood":             # EmbedHg2vNeighborhoodWeightedJaccard, :369-377
+    n2f, e2f = W.WeightByNeighborhood(hc, 0.25)
+  else:                                            # distance features of the HOBE weighting
+    n2f, e2f = W.WeightByDistance(hc, 0.3, arrays_to_emb(ref, xn, xe), np.linalg.norm, True)
+  np.random.seed(seed)
+  t = time.time()
+  recs = ref.hg2v_sample.WeightedJaccardSamples(hc, n2f, e2f, k, num_samples,
+                                                run_in_parallel=False, disable_pbar=True)
+  dt = time.time() - t
+  state = np.random.get_state()
+  arr = port.records_to_arrays(recs, k)
+  lw = np.asarray([np.nan if r.left_weight is None else r.left_weight for r in recs], np.float32)
+  rw = np.asarray([np.nan if r.right_weight is None else r.right_weight for r in recs], np.float32)
+  out = dict(pairs=incidence_pairs(hc), k=k, num_samples=num_samples, seed=seed, count=len(recs),
+             feature_kind=feature_kind, node_rows=np.asarray(list(hc.node)),
+             edge_rows=np.asarray(list(hc.edge)), rng_pos=state[2],
+             rng_key_sha=hashlib.sha256(state[1].tobytes()).hexdigest(), ref_seconds=dt,
+             col_left_weight=lw, col_right_weight=rw)
+  for tag, m in (("n2f", n2f), ("e2f", e2f)):
+    for key, v in csr_parts(m).items():
+      out["%s_%s" % (tag, key)] = v
+  for key, v in arr.items():
+    out["col_" + key] = v.astype(np.float32) if "prob" in key else v.astype(np.int32)
+  save("jaccard_" + name, **out)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--only", default=None)
@@ -242,6 +275,12 @@ def main():
              seed=10, parallel=False, stride=1)
     gen_hobe(ref, "youtube_s2", g["youtube"], *embs["youtube"], k=5,
              num_samples=2, seed=11, parallel=False, stride=1)
+  if want("jaccard"):
+    gen_jaccard(ref, "tiny_uniform", g["tiny"], "uniform", 2, 3, 12)
+    gen_jaccard(ref, "rand25_uniform", g["rand25"], "uniform", 3, 5, 13)
+    gen_jaccard(ref, "rand25_neighborhood", g["rand25"], "neighborhood", 3, 5, 14)
+    gen_jaccard(ref, "rand25_distance", g["rand25"], "distance", 3, 5, 15, *embs["rand25"])
+    gen_jaccard(ref, "youtube_s2_neighborhood", g["youtube"], "neighborhood", 5, 2, 16)
   if want("hobe_full"):
     # BASELINE.json configs[0]: defaults of embedding.py:389-397.  Pair sets and
     # probabilities are deterministic with run_in_parallel=True; neighbour
