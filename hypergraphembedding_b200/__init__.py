@@ -13,6 +13,9 @@ from .algebraic_distance import EmbedAlgebraicDistance
 from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, BooleanSamplesCsr,
                           SampleColumns, SamplesToModelInput, SimilarityRecord,
                           SparseWeightedJaccard, WeightedJaccardSamples)
+from .hg2v_model import BooleanModel, KerasModelToEmbedding, UnweightedFloatModel
+from .embedding import (EMBEDDING_OPTIONS, EmbedHg2vAdjJaccard, EmbedHg2vAlgDist, EmbedHg2vBoolean,
+                        EmbedHg2vNeighborhoodWeightedJaccard)
 from .hg2v_weighting import (AlphaScaleValues, ComputeSpans, DictToSparseRow, OneMinusValues,
                              UniformWeight, WeightByAlgebraicSpan, WeightByDistance,
                              WeightByDistanceCluster, WeightByNeighborhood,
@@ -24,6 +27,9 @@ __all__ = [
     "EmbedAlgebraicDistance",
     "AlgebraicDistanceSamples", "BooleanSamples", "BooleanSamplesCsr", "SampleColumns",
     "SamplesToModelInput", "SimilarityRecord", "SparseWeightedJaccard", "WeightedJaccardSamples",
+    "BooleanModel", "UnweightedFloatModel", "KerasModelToEmbedding", "EMBEDDING_OPTIONS",
+    "EmbedHg2vBoolean", "EmbedHg2vAdjJaccard", "EmbedHg2vNeighborhoodWeightedJaccard",
+    "EmbedHg2vAlgDist",
     "AlphaScaleValues", "ComputeSpans", "DictToSparseRow", "OneMinusValues", "UniformWeight",
     "WeightByAlgebraicSpan", "WeightByDistance", "WeightByDistanceCluster", "WeightByNeighborhood",
     "WeightBySameTypeDistance", "ZeroOneScaleValues",

@@ -103,6 +103,14 @@ SIGNATURES = {
                                             c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp,
                                             c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp,
                                             ctypes.c_int64, c_vp, ctypes.c_int]),
+    "hge_hg2v_create": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int,
+                                       ctypes.POINTER(c_vp)]),
+    "hge_hg2v_destroy": (ctypes.c_int, [c_vp]),
+    "hge_hg2v_set_samples": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int]),
+    "hge_hg2v_fit_epoch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_double)]),
+    "hge_hg2v_get_weights": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
     "hge_mt19937_random_raw": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp]),
     "hge_mt19937_interval": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_int64, c_vp]),
     "hge_spgemm_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

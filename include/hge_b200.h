@@ -269,6 +269,32 @@ int hge_sample_neighbors(const int64_t* n2e_ptr, const int32_t* n2e_idx, const i
                          int64_t num_samples, int k, uint32_t* state625, int32_t* out_nbr_edges,
                          int32_t* out_nbr_nodes);
 
+/* ---- hypergraph2vec training (hg2v_model.py:51-203, fit loop embedding.py:269-305) ---------
+ * The consumer of the sample columns.  Two embedding tables [rows, dim] fp32 whose row 0 is the
+ * trained padding row (Embedding(input_dim = max id + 2)); outputs
+ *   node_node = act(<N[ln], N[rn]>), edge_edge = act(<E[le], E[re]>),
+ *   node_edge = mean_i act(<N[nn_i], N[ln]>) * mean_i act(<E[ne_i], E[re]>);
+ * activation 0 = sigmoid (BooleanModel), 1 = relu (UnweightedFloatModel); loss 0 = Keras
+ * kullback_leibler_divergence, 1 = mean_squared_error, summed over the three outputs; optimizer =
+ * Keras Adagrad defaults (lr 0.01, epsilon 1e-7).  One call of hge_hg2v_fit_epoch is one epoch:
+ * consecutive batches of `batch_size` samples taken in the given order, one kernel launch. */
+typedef struct hge_hg2v_model hge_hg2v_model;
+int hge_hg2v_create(hge_ctx* ctx, int32_t node_rows, int32_t edge_rows, int dim, int num_neighbors,
+                    int activation, int loss, const float* node_init, const float* edge_init,
+                    int mem, hge_hg2v_model** out);
+int hge_hg2v_destroy(hge_hg2v_model* m);
+/* features: int32 [4 + 2 * num_neighbors][num_samples], the columns of SamplesToModelInput
+ * (hg2v_sample.py:751-797, weighted = False): left node, left edge, right node, right edge,
+ * nodes_in_edge_0.., edges_containing_node_0.. (0 = padding row); targets: fp32
+ * [3][num_samples] = node_node, edge_edge, node_edge probabilities. */
+int hge_hg2v_set_samples(hge_hg2v_model* m, const int32_t* features, const float* targets,
+                         int64_t num_samples, int mem);
+/* order: int32 [num_samples] permutation (Keras: np.random.shuffle per epoch).  *epoch_loss =
+ * sample-weighted mean of the batch losses (what EarlyStopping(monitor="loss") watches). */
+int hge_hg2v_fit_epoch(hge_hg2v_model* m, const int32_t* order, int batch_size, int mem,
+                       double* epoch_loss);
+int hge_hg2v_get_weights(hge_hg2v_model* m, float* node, float* edge, int mem);
+
 /* ---- hypergraph.proto wire format (host code; all pointers are host pointers) --------------
  * The data formats either side of the path: a serialized Hypergraph (hypergraph.proto:6-23) is
  * read straight into arrays, replacing the per-incidence Python loops of ToCsrMatrix /
