@@ -273,6 +273,46 @@ def hobe_extra(ctx):
           "fobe_records": len(fobe), "fobe_samples_per_s": len(fobe) / fobe_s}
 
 
+def hg2v_train_extra(ctx, dimension=32, epochs=3):
+  """The consumer of the HOBE sample columns: UnweightedFloatModel (hg2v_model.py:129-203) trained
+  on the 755 267 configs[0] records with the reference's fit settings (batch 256, Adagrad;
+  embedding.py:387-414); dimension 32 (runner.py asks for a dimension below the 50 edges)."""
+  import hypergraphembedding_b200 as H
+  path = os.path.join(ROOT, "tests", "golden", "algdist_youtube.npz")
+  g = np.load(path)
+  node_ids, edge_ids = g["node_ids"], g["edge_ids"]
+  hg = H.Hypergraph()
+  emb = H.HypergraphEmbedding()
+  for n, e in zip(np.searchsorted(node_ids, g["pairs"][:, 0]).tolist(),
+                  np.searchsorted(edge_ids, g["pairs"][:, 1]).tolist()):
+    hg.node[n].edges.append(e)
+    hg.edge[e].nodes.append(n)
+  for i, v in enumerate(g["xn"]):
+    emb.node[i].values.extend(v.tolist())
+  for i, v in enumerate(g["xe"]):
+    emb.edge[i].values.extend(v.tolist())
+  np.random.seed(0)
+  samples = H.AlgebraicDistanceSamples(hg, emb, 5, 200)
+  feats, targets = H.SamplesToModelInput(samples, 5, weighted=False)
+  model = H.UnweightedFloatModel(hg, dimension, 5)
+  model.set_samples(feats, targets)
+  m = len(samples)
+  model.fit_epoch(np.random.permutation(m), 256)          # warm-up epoch
+  secs, losses = [], []
+  for _ in range(epochs):
+    order = np.random.permutation(m)
+    t = time.perf_counter()
+    losses.append(model.fit_epoch(order, 256))
+    secs.append(time.perf_counter() - t)
+  model.close()
+  batches = (m + 255) // 256
+  return {"workload": "UnweightedFloatModel on the %d HOBE records of snap_youtube_tiny, dimension %d, "
+                      "num_neighbors 5, batch 256, Adagrad" % (m, dimension),
+          "samples_per_s": m / min(secs), "epoch_s": min(secs), "us_per_batch": 1e6 * min(secs) / batches,
+          "batches_per_epoch": batches, "epoch_losses": losses,
+          "kernel": "k_hg2v_epoch: one launch per epoch, one 8-CTA cluster, 2 cluster barriers per batch"}
+
+
 def pair_weighting_extra(ctx, num_pairs=100000000):
   """BASELINE.json configs[2]: AMiner-shaped bipartite hypergraph, R=64, distance + HOBE weight
   transform of 100M sampled (node, edge) pairs, everything resident on the device."""
@@ -516,7 +556,8 @@ def run_ours(args, spec):
   cpu_value, cpu_dt, cpu_threads = cpu_baseline_port(A, B, spec, cpu_sweeps)
   extras = {}
   if not args.no_extras:
-    for key, fn in (("hobe", hobe_extra), ("pair_weighting", pair_weighting_extra)):
+    for key, fn in (("hobe", hobe_extra), ("hg2v_train", hg2v_train_extra),
+                    ("pair_weighting", pair_weighting_extra)):
       try:
         extras[key] = fn(ctx)
       except Exception as exc:   # the headline line must survive a failing side measurement
