@@ -834,10 +834,12 @@ def run_sharded(args, spec, world, rank, local_rank):
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
   h_xn0, h_xe0 = pin(xn0), pin(xe0)
   h_xn, h_xe = pin(np.empty_like(xn0)), pin(np.empty_like(xe0))
+  h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32)),
+           pin(B.indptr.astype(np.int64)), pin(B.indices.astype(np.int32))]
 
   def step_host():
-    r = hd.ShardedRelaxation(A, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
-                             B_local=B)
+    r = hd.ShardedRelaxation(None, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
+                             shape=(n_loc, E), csr_host=[t.numpy() for t in h_csr])
     r.run(h_xn.numpy(), h_xe.numpy())
     r.close()
 

@@ -82,18 +82,20 @@ class NativeOps(object):
   """The per-rank kernels of libhge_b200.so behind the interface ShardedRelaxation drives."""
 
   def __init__(self, A_local, R, iterations, num_slices, ctx=None, B_local=None, shape=None,
-               csr_device=None):
-    """A_local: scipy n_local x E incidence block (B_local: its transpose, optional), or
-    csr_device = (n2e_ptr, n2e_idx, e2n_ptr, e2n_idx) torch CUDA tensors with shape=(n_local, E)."""
+               csr_device=None, csr_host=None):
+    """A_local: scipy n_local x E incidence block (B_local: its transpose, optional), or, with
+    shape=(n_local, E), csr_device = (n2e_ptr, n2e_idx, e2n_ptr, e2n_idx) torch CUDA tensors or
+    csr_host = the same four as int64 / int32 numpy arrays (e.g. views of pinned memory, which
+    upload at full PCIe speed; scipy's own arrays are pageable)."""
     import torch
     self.torch = torch
     self.ctx = ctx or _native.default_context()
     self.device = torch.device("cuda", self.ctx.device)
     self.R, self.iterations = R, iterations
-    if csr_device is not None:
+    if csr_device is not None or csr_host is not None:
       n_loc, num_edges = shape
-      self.inc = _native.Incidence(self.ctx, n_loc, num_edges, *csr_device, sharded=True,
-                                   num_slices=num_slices)
+      self.inc = _native.Incidence(self.ctx, n_loc, num_edges, *(csr_device or csr_host),
+                                   sharded=True, num_slices=num_slices)
     else:
       A = sps.csr_matrix(A_local)
       if B_local is None:
