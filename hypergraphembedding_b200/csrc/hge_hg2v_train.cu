@@ -149,15 +149,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   __syncthreads();
   double loss_total = 0.0;
   const int64_t num_batches = (a.M + a.batch - 1) / a.batch;
+  // the indices / targets of this warp's first sample of a batch are fetched one batch ahead
+  // (during phase 2 of the previous one) and kept for phase 2: two dependent global loads
+  // (order -> feature columns) less on the critical path of every phase
+  auto fetch = [&](int64_t first, int bs, int s, int32_t* my, float* my_t) {
+    *my = 0;
+    *my_t = 0.0f;
+    if (s < bs) {
+      const int64_t sample = a.order[first + s];
+      if (lane < cols) *my = a.feat[(size_t)lane * a.M + sample];
+      if (lane < 3) *my_t = a.target[(size_t)lane * a.M + sample];
+    }
+  };
+  int32_t my_first, my_next = 0;
+  float my_t_first, my_t_next = 0.0f;
+  fetch(0, (int)min((int64_t)a.batch, a.M), warp, &my_first, &my_t_first);
   for (int64_t b = 0; b < num_batches; ++b) {
     const int64_t first = b * a.batch;
     const int bs = (int)min((int64_t)a.batch, a.M - first);
     const float inv_bs = 1.0f / (float)bs;
     // ---- phase 1: forward + backward ----------------------------------------------------
     for (int s = warp; s < bs; s += num_warps) {
-      const int64_t sample = a.order[first + s];
-      const int32_t my = lane < cols ? a.feat[(size_t)lane * a.M + sample] : 0;
-      const float my_t = lane < 3 ? a.target[(size_t)lane * a.M + sample] : 0.0f;
+      int32_t my = my_first;
+      float my_t = my_t_first;
+      if (s != warp) fetch(first, bs, s, &my, &my_t);
       const int32_t ln = __shfl_sync(kFull, my, 0), le = __shfl_sync(kFull, my, 1);
       const int32_t rn = __shfl_sync(kFull, my, 2), re = __shfl_sync(kFull, my, 3);
       float Ln[DPL], Rn[DPL], Le[DPL], Re[DPL], X[DPL];
@@ -228,13 +243,20 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       if (v != 0.0f) atomicAdd((t ? a.gE : a.gN) + cc, v);
       s_g0[t][cc] = 0.0f;
     }
-    __threadfence();
+    // barrier.cluster arrive.release / wait.acquire: every CTA that touches the tables is in
+    // this cluster, so cluster scope orders the gradient atomics before the updates below
     cluster.sync();
+    if (b + 1 < num_batches)
+      fetch(first + a.batch, (int)min((int64_t)a.batch, a.M - first - a.batch), warp, &my_next,
+            &my_t_next);
     // ---- phase 2: Adagrad on the rows this warp's samples touched ------------------------
     const int32_t stamp = a.batch_id0 + (int32_t)b;
     for (int s = warp; s < bs; s += num_warps) {
-      const int64_t sample = a.order[first + s];
-      const int32_t my = lane < cols ? a.feat[(size_t)lane * a.M + sample] : 0;
+      int32_t my = my_first;
+      if (s != warp) {
+        float unused;
+        fetch(first, bs, s, &my, &unused);
+      }
       // column c of the sample indexes the node table for c in {0, 2, 4 .. 4+k-1}
       int32_t old = stamp;
       if (lane < cols) {
@@ -249,8 +271,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         else apply_row(a.E, a.accE, a.gE, row, dim, lane, a.lr, a.eps);
       }
     }
-    __threadfence();
     cluster.sync();
+    my_first = my_next;
+    my_t_first = my_t_next;
   }
   if (lane == 0 && loss_total != 0.0) atomicAdd(a.loss_sum, loss_total);
 }
