@@ -232,7 +232,7 @@ class RowPipeline {
               const int32_t* rows, int64_t num_rows, int threads)
       : rows_(rows), num_rows_(num_rows) {
     num_blocks_ = (num_rows + kBlockRows - 1) / kBlockRows;
-    depth_ = std::max<int64_t>(2, 3 * (int64_t)threads);
+    depth_ = std::max<int64_t>(4, 8 * (int64_t)threads);
     slots_.resize((size_t)depth_);
     for (int t = 0; t < threads; ++t)
       workers_.emplace_back([=] { work(kind, m1, m2, m3, mid_cols, out_cols); });
@@ -263,7 +263,7 @@ class RowPipeline {
   }
 
  private:
-  static const int64_t kBlockRows = 1024;
+  static const int64_t kBlockRows = 64;   // small blocks: the consumer starts after 64 rows
   struct Slot {
     std::vector<int64_t> ptr;
     std::vector<int32_t> idx;
@@ -330,8 +330,10 @@ int sampler_threads_for(int kind, int64_t num_rows) {
     if (env && *env) n = atoi(env);
   }
   if (n == 0) {
-    if (kind == 0 || num_rows < 16384) return 1;   // small jobs: thread start-up costs more
-    n = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (kind == 0 || num_rows < 512) return 1;   // small jobs: thread start-up costs more
+    // the single consumer (the draw loop) keeps up with about three row builders
+    n = (int)std::min<unsigned>(num_rows < 16384 ? 4u : 16u,
+                                std::max(1u, std::thread::hardware_concurrency()));
   }
   return std::max(1, n);
 }

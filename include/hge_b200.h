@@ -257,8 +257,9 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
                         int64_t* out_count);
 
 /* Worker threads that build candidate rows ahead of the (sequential) draw loop of
- * hge_sample_adj_rows: 0 = automatic (one thread for small jobs, up to 16 for >= 16K product
- * rows; HGE_SAMPLER_THREADS overrides), 1 = build rows inline.  Results do not depend on it. */
+ * hge_sample_adj_rows: 0 = automatic (inline below 512 product rows, up to 4 threads below 16K
+ * rows, up to 16 above; HGE_SAMPLER_THREADS overrides), 1 = build rows inline.  Results do not
+ * depend on it. */
 int hge_sampler_set_threads(int threads);
 
 /* _sample_neighbors (hg2v_sample.py:49-51) for a list of (node, edge) samples: per sample k
