@@ -52,6 +52,7 @@ SIGNATURES = {
     "hge_ctx_sync": (ctypes.c_int, [c_vp]),
     "hge_ctx_set_tuning": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hge_ctx_set_bulk": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "hge_ctx_set_tile_mb": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hge_ctx_launch_count": (ctypes.c_int64, [c_vp]),
     "hge_incidence_create": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp,
                                             c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
@@ -214,6 +215,9 @@ class Context(object):
 
   def set_tuning(self, light_max_deg=0, chunk=0, blocks_per_sm=0):
     check(self.lib.hge_ctx_set_tuning(self.handle, light_max_deg, chunk, blocks_per_sm))
+
+  def set_tile_mb(self, tile_mb, min_rows_mb=1024):
+    check(self.lib.hge_ctx_set_tile_mb(self.handle, int(tile_mb), int(min_rows_mb)))
 
   def set_bulk(self, enabled):
     check(self.lib.hge_ctx_set_bulk(self.handle, 1 if enabled else 0))

@@ -117,6 +117,32 @@ __global__ void k_invert(int32_t rows, const double* __restrict__ wsum, float* _
     invs[r] = (float)(1.0 / wsum[r]);
 }
 
+// pos[t * rows + r] = first incidence of row r whose column id is >= t * tile_cols, for
+// t = 0 .. tiles (column ids are sorted inside a row): the sub-range of row r that falls into
+// column tile t is [pos[t][r], pos[t + 1][r]).
+__global__ void k_tile_offsets(int32_t rows, const int64_t* __restrict__ ptr,
+                               const int32_t* __restrict__ idx, int tiles, int32_t tile_cols,
+                               int64_t* __restrict__ pos) {
+  const int64_t total = (int64_t)rows * (tiles + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i / rows);
+    const int32_t r = (int32_t)(i - (int64_t)t * rows);
+    const int64_t b = ptr[r], e = ptr[r + 1];
+    int64_t lo = b, hi = e;
+    if (t == 0) hi = b;
+    else if (t == tiles) lo = e;
+    else {
+      const int64_t want = (int64_t)t * tile_cols;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid] < want) lo = mid + 1; else hi = mid;
+      }
+    }
+    pos[i] = lo;
+  }
+}
+
 __global__ void k_fill_minmax(int32_t* mm, int slots, int ld) {
   const int n = slots * 2 * ld;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -176,7 +202,8 @@ struct HalfSweepArgs {
   const int32_t* mm_prev;      // affine of the previous sweep, or nullptr (identity)
   int32_t* mm_cur;             // min / max slots of this sweep
   int32_t gather_affine;       // 1: gathered rows carry the previous sweep's affine (node half)
-  int32_t raw_out;             // 1: write the raw gathered sums to raw[rows, ld4] (sharded edge half)
+  int32_t raw_out;             // 1: write the raw gathered sums to raw[rows, ld4] (sharded edge half);
+                               // 3: add them to raw (later node-range tiles of the edge half)
   float4* raw;
   // raw_out == 2: peer-memory push.  Row r belongs to rank r / push_rows; its raw sums go to
   // that rank's staging block  push_stage[owner] + (push_rank * push_rows + r % push_rows) rows
@@ -326,6 +353,12 @@ struct RowOwner {
         float4* dst = a.push_stage[owner] +
                       ((size_t)a.push_rank * a.push_rows + (row - owner * a.push_rows)) * ld4 + c4;
         *dst = acc;
+      } else if (a.raw_out == 3) {
+        // node-range tiles of the edge half: this tile's sum joins the earlier tiles' (one
+        // owner per row and launch, so a plain read-modify-write)
+        float4 prev = a.raw[off];
+        hge_f4_add(prev, acc);
+        a.raw[off] = prev;
       } else {
         a.raw[off] = acc;
       }
@@ -822,10 +855,12 @@ int occupancy_grid(const hge_ctx* ctx, int* out) {
 }
 
 int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice = -1,
-             const hge_p2p* push = nullptr) {
+             const hge_p2p* push = nullptr, const HgeHalfSchedule* tile = nullptr,
+             bool accumulate = false) {
   hge_incidence* inc = st->inc;
-  const HgeHalfSchedule& s = node_half ? inc->node_half
-                                       : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
+  const HgeHalfSchedule& s = tile ? *tile
+                             : node_half ? inc->node_half
+                                         : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
   HalfSweepArgs a;
   a.idx = s.idx;
   a.yg = reinterpret_cast<const float4*>(node_half ? st->ye : st->yn);
@@ -842,7 +877,7 @@ int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice =
   a.mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
   a.mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
   a.gather_affine = node_half ? 1 : 0;
-  a.raw_out = push ? 2 : (raw ? 1 : 0);
+  a.raw_out = push ? 2 : (raw ? (accumulate ? 3 : 1) : 0);
   a.raw = reinterpret_cast<float4*>(raw);
   a.push_stage = push ? push->d_peer_stage : nullptr;
   a.push_rows = push ? push->own_rows : 1;
@@ -1057,6 +1092,9 @@ int hge_incidence_destroy(hge_incidence* inc) {
   free_half_schedule(ctx, &inc->edge_half);
   for (HgeHalfSchedule& sl : inc->edge_slices) free_half_schedule(ctx, &sl, false);
   inc->edge_slices.clear();
+  for (HgeHalfSchedule& tl : inc->edge_tiles) free_half_schedule(ctx, &tl, false);
+  inc->edge_tiles.clear();
+  hge_dev_free(ctx, inc->tile_pos);
   hge_dev_free(ctx, inc->edge_wsum);
   if (inc->owns_csr) {
     hge_dev_free(ctx, inc->n2e_ptr);
@@ -1069,6 +1107,38 @@ int hge_incidence_destroy(hge_incidence* inc) {
 }
 
 int64_t hge_incidence_nnz(const hge_incidence* inc) { return inc ? inc->node_half.nnz : 0; }
+
+// Builds (once per tile height) the node-range tiles of the edge half: per tile a schedule over
+// all edges whose rows are the sub-ranges of the member lists that fall into the tile.
+static int ensure_edge_tiles(hge_ctx* ctx, hge_incidence* inc, int32_t tile_rows) {
+  if (inc->tile_rows == tile_rows && !inc->edge_tiles.empty()) return HGE_OK;
+  for (HgeHalfSchedule& tl : inc->edge_tiles) free_half_schedule(ctx, &tl, false);
+  inc->edge_tiles.clear();
+  hge_dev_free(ctx, inc->tile_pos);
+  inc->tile_rows = tile_rows;
+  const int tiles = (int)(((int64_t)inc->N + tile_rows - 1) / tile_rows);
+  if (tiles <= 1) return HGE_OK;
+  const HgeHalfSchedule& eh = inc->edge_half;
+  HGE_TRY(hge_dev_alloc(ctx, &inc->tile_pos, (size_t)(tiles + 1) * inc->E));
+  k_tile_offsets<<<grid_1d(ctx, (int64_t)inc->E * (tiles + 1), kBlock), kBlock, 0, ctx->stream>>>(
+      inc->E, inc->e2n_ptr, inc->e2n_idx, tiles, tile_rows, inc->tile_pos);
+  HGE_CHECK_LAUNCH(ctx);
+  inc->edge_tiles.resize((size_t)tiles);
+  for (int t = 0; t < tiles; ++t) {
+    inc->edge_tiles[(size_t)t].skip_empty = true;
+    HGE_TRY(hge_sched_begin_ranges(ctx, 0, inc->E, inc->tile_pos + (size_t)t * inc->E,
+                                   inc->tile_pos + (size_t)(t + 1) * inc->E, tile_rows,
+                                   &inc->edge_tiles[(size_t)t]));
+  }
+  for (int t = 0; t < tiles; ++t) {
+    HgeHalfSchedule& tl = inc->edge_tiles[(size_t)t];
+    tl.idx = eh.idx;
+    tl.deg = eh.deg;
+    tl.invs = eh.invs;
+    HGE_TRY(hge_sched_finish(ctx, "edge tile", &tl));
+  }
+  return HGE_OK;
+}
 
 int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iterations,
                        hge_algdist** out) {
@@ -1107,8 +1177,25 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   if ((rc = hge_dev_alloc(ctx, &st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
   if ((rc = hge_dev_alloc(ctx, &st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
     return fail(rc);
+  // single GPU, node rows far beyond what random gathers reach at full rate: tile the edge half
+  if (!inc->sharded && ctx->tile_mb > 0) {
+    const int64_t tile_rows64 = ((int64_t)ctx->tile_mb << 20) / ((int64_t)st->ld * 4);
+    const int32_t tile_rows = (int32_t)std::max<int64_t>(1, std::min<int64_t>(tile_rows64, INT32_MAX));
+    const int64_t row_bytes = (int64_t)inc->N * st->ld * 4;
+    if (row_bytes > ((int64_t)ctx->tile_min_mb << 20) && (int64_t)inc->N > 2 * (int64_t)tile_rows) {
+      if ((rc = ensure_edge_tiles(ctx, inc, tile_rows)) != HGE_OK) return fail(rc);
+      if (!inc->edge_tiles.empty() &&
+          (rc = hge_dev_alloc(ctx, &st->tile_raw, (size_t)inc->E * st->ld)) != HGE_OK)
+        return fail(rc);
+    }
+  }
   size_t n_part = (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials);
   size_t n_cnt = (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows);
+  if (st->tile_raw)
+    for (const HgeHalfSchedule& tl : inc->edge_tiles) {
+      n_part = std::max(n_part, (size_t)tl.n_partials);
+      n_cnt = std::max(n_cnt, (size_t)tl.n_hrows);
+    }
   for (const HgeHalfSchedule& sl : inc->edge_slices) {
     n_part = std::max(n_part, (size_t)sl.n_partials);
     n_cnt = std::max(n_cnt, (size_t)sl.n_hrows);
@@ -1142,6 +1229,7 @@ int hge_algdist_destroy(hge_algdist* st) {
   if (st->owns_ye) hge_dev_free(ctx, st->ye);
   hge_dev_free(ctx, st->mm);
   hge_dev_free(ctx, st->partials);
+  hge_dev_free(ctx, st->tile_raw);
   hge_dev_free(ctx, st->counters);
   delete st;
   return HGE_OK;
@@ -1195,7 +1283,22 @@ int hge_algdist_node_half(hge_algdist* st, int sweep) {
 int hge_algdist_edge_half(hge_algdist* st, int sweep) {
   HGE_REQUIRE(st && sweep >= 0 && sweep < st->max_iters, "hge_algdist_edge_half: bad sweep %d", sweep);
   HGE_CUDA(cudaSetDevice(st->ctx->device));
-  return run_half(st, false, sweep, nullptr);
+  if (!st->tile_raw) return run_half(st, false, sweep, nullptr);
+  // tiled: every tile adds the sums of its node range to tile_raw, then one pass blends,
+  // rescales and stores the edge rows (the kernel the sharded path uses after its all-reduce)
+  hge_ctx* ctx = st->ctx;
+  hge_incidence* inc = st->inc;
+  HGE_CUDA(cudaMemsetAsync(st->tile_raw, 0, (size_t)inc->E * st->ld * sizeof(float), ctx->stream));
+  for (size_t t = 0; t < inc->edge_tiles.size(); ++t)
+    HGE_TRY(run_half(st, false, sweep, st->tile_raw, -1, nullptr, &inc->edge_tiles[t], true));
+  HGE_REQUIRE(st->ld <= 1024, "hge_algdist_edge_half: dimension too large for the tiled edge half");
+  const int32_t* mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
+  int32_t* mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
+  k_edge_finalize<<<grid_1d(ctx, (int64_t)inc->E * st->ld, kBlock), kBlock, 0, ctx->stream>>>(
+      0, inc->E, st->R, st->ld, st->tile_raw, inc->edge_half.deg, inc->edge_half.invs, mm_prev, mm_cur,
+      st->ye);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
 }
 
 int hge_algdist_edge_partial(hge_algdist* st, int sweep, int slice, float* partial) {

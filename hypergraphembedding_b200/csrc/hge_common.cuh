@@ -51,8 +51,10 @@ struct hge_ctx {
   int chunk;
   int blocks_per_sm;
   int use_bulk;          // long rows through the bulk-copy engine (k_heavy_bulk)
+  int tile_mb;           // node-range tile of the single-GPU edge half in MB of rows (0 = off)
+  int tile_min_mb;       // ... used when the node rows exceed this many MB
   int64_t launches;
-  // ring of 64-byte pinned host slots for small device -> host read-backs (schedule statistics)
+  // ring of 128-byte pinned host slots for small device -> host read-backs (schedule statistics)
   char* pinned_ring;
   int pinned_next;
   // host-buffer calls: dense staging block on the device (grow-only) and a copy stream, so the
@@ -67,7 +69,7 @@ struct hge_ctx {
 // Staging block of at least `floats` floats (contents undefined).  Growing it drains the stream.
 int hge_ctx_stage(hge_ctx* ctx, size_t floats, float** out);
 
-// One 64-byte pinned host slot; slots are handed out round-robin from a ring of 256, so a slot
+// One 128-byte pinned host slot; slots are handed out round-robin from a ring of 256, so a slot
 // stays untouched until 255 later requests on the same context.  nullptr on failure.
 void* hge_ctx_pinned_slot(hge_ctx* ctx);
 

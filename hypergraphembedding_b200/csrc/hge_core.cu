@@ -19,7 +19,7 @@ void hge_set_error(const char* fmt, ...) {
 void* hge_ctx_pinned_slot(hge_ctx* ctx) {
   if (!ctx->pinned_ring) {
     void* p = nullptr;
-    if (cudaMallocHost(&p, 256 * 64) != cudaSuccess) {
+    if (cudaMallocHost(&p, 256 * 128) != cudaSuccess) {
       cudaGetLastError();
       hge_set_error("cudaMallocHost of the pinned slot ring failed");
       return nullptr;
@@ -27,7 +27,7 @@ void* hge_ctx_pinned_slot(hge_ctx* ctx) {
     ctx->pinned_ring = static_cast<char*>(p);
     ctx->pinned_next = 0;
   }
-  char* slot = ctx->pinned_ring + (size_t)(ctx->pinned_next & 255) * 64;
+  char* slot = ctx->pinned_ring + (size_t)(ctx->pinned_next & 255) * 128;
   ctx->pinned_next++;
   return slot;
 }
@@ -94,6 +94,13 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   // measured slower than the register gather (profiles/r1_bulk_copy_experiment.md): opt-in
   ctx->use_bulk = 0;
   if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;
+  // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
+  // the single-GPU edge half over more than 1 GB of node rows is tiled by node range into
+  // L2-sized tiles (profiles/r1_tiled_edge_half.md)
+  ctx->tile_mb = 64;
+  ctx->tile_min_mb = 1024;
+  if (const char* env = getenv("HGE_TILE_MB")) ctx->tile_mb = atoi(env);
+  if (const char* env = getenv("HGE_TILE_MIN_MB")) ctx->tile_min_mb = atoi(env);
   ctx->launches = 0;
   ctx->pinned_ring = nullptr;
   ctx->pinned_next = 0;
@@ -163,6 +170,15 @@ int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_pe
   if (light_max_deg) ctx->light_max_deg = light_max_deg;
   if (chunk) ctx->chunk = chunk;
   ctx->blocks_per_sm = blocks_per_sm;
+  return HGE_OK;
+}
+
+int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb) {
+  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_tile_mb: ctx is NULL");
+  HGE_REQUIRE(tile_mb >= 0 && tile_mb <= (1 << 20) && min_rows_mb >= 0 && min_rows_mb <= (1 << 20),
+              "hge_ctx_set_tile_mb: %d / %d MB not in [0, 2^20]", tile_mb, min_rows_mb);
+  ctx->tile_mb = tile_mb;
+  ctx->tile_min_mb = min_rows_mb;
   return HGE_OK;
 }
 

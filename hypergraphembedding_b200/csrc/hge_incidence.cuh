@@ -33,7 +33,10 @@ struct HgeHeavyRow {    // 32 B
 struct HgeHalfSchedule {
   int32_t rows = 0;
   int64_t nnz = 0;
-  const int64_t* ptr = nullptr;   // device CSR row pointers [rows + 1]
+  const int64_t* ptr = nullptr;   // device CSR row pointers [rows + 1] (= first incidence per row)
+  const int64_t* row_end = nullptr;  // one past the last incidence per row (ptr + 1 for a plain CSR)
+  bool ranges = false;            // rows are sub-ranges of CSR rows (node-range tiles)
+  bool skip_empty = false;        // leave rows without incidences out of the work items
   const int32_t* idx = nullptr;   // device CSR column ids [nnz]
   int32_t* deg = nullptr;         // device, weight degree of each row (global degree if sharded)
   float* invs = nullptr;          // device, 1 / sum_b (1 / deg_other[b]) per row
@@ -60,6 +63,11 @@ struct HgeHalfSchedule {
 // the work items (needs s->invs).  release frees everything the two allocated.
 int hge_sched_begin(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* d_ptr,
                     int64_t max_degree_possible, HgeHalfSchedule* s);
+// The same for rows given as [row_begin[r], row_end[r]) ranges of a column-id array (sub-ranges
+// of CSR rows: the node-range tiles of the edge half).
+int hge_sched_begin_ranges(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* row_begin,
+                           const int64_t* row_end, int64_t max_degree_possible,
+                           HgeHalfSchedule* s);
 int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s);
 void hge_sched_release(const hge_ctx* ctx, HgeHalfSchedule* s);
 
@@ -82,6 +90,12 @@ struct hge_incidence {
   std::vector<HgeHalfSchedule> edge_slices;
   std::vector<int32_t> slice_bounds;
   hge_algdist* cached = nullptr;   // workspace of the last hge_algdist_run, re-used across calls
+  // Node-range tiles of the edge half (single GPU, node rows beyond the TLB reach of random
+  // gathers): tile t gathers only the members in [t * tile_rows, (t + 1) * tile_rows) of every
+  // edge.  Built on first use by hge_algdist_create (the tile height depends on R).
+  std::vector<HgeHalfSchedule> edge_tiles;
+  int64_t* tile_pos = nullptr;     // device [(tiles + 1) x E] incidence offsets
+  int32_t tile_rows = 0;
 };
 
 int hge_incidence_host_ptr(hge_incidence* inc, int order, const std::vector<int64_t>** out);
@@ -114,6 +128,7 @@ struct hge_algdist {
   float* ye = nullptr;
   bool owns_ye = true;          // false: ye lives in a peer-memory arena
   int32_t* mm = nullptr;        // [max_iters][2][ld]
+  float* tile_raw = nullptr;    // [E, ld] un-normalised edge sums accumulated over the tiles
   float4* partials = nullptr;   // max over the two halves
   int32_t* counters = nullptr;
   int grid = 0;

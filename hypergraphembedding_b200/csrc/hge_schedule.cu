@@ -24,8 +24,8 @@ namespace {
 
 constexpr int kBlock = 256;
 
-enum { kHeavy = 0, kChunks, kPartials, kMaxDeg, kFirstEmpty, kBadRow, kNnz, kFirstPtr, kStatWords };
-static_assert(kStatWords * sizeof(long long) <= 64, "statistics must fit one pinned slot");
+enum { kHeavy = 0, kChunks, kPartials, kMaxDeg, kFirstEmpty, kBadRow, kNnz, kFirstPtr, kEmpty, kStatWords };
+static_assert(kStatWords * sizeof(long long) <= 128, "statistics must fit one pinned slot");
 
 __global__ void k_sched_init(long long* stats) {
   if (threadIdx.x < kStatWords)
@@ -34,24 +34,29 @@ __global__ void k_sched_init(long long* stats) {
 
 // key = key_max - degree (ascending key = descending degree), value = row id; statistics of
 // the row range by block reduction + one atomic per block.
-__global__ void k_sched_keys(int32_t row0, int32_t rows, const int64_t* __restrict__ ptr,
-                             int light_max, int chunk, uint32_t key_max,
+__global__ void k_sched_keys(int32_t row0, int32_t rows, const int64_t* __restrict__ rb,
+                             const int64_t* __restrict__ re, int light_max, int chunk,
+                             uint32_t key_max,
                              uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
                              long long* stats) {
-  long long heavy = 0, chunks = 0, partials = 0, max_deg = 0;
+  long long heavy = 0, chunks = 0, partials = 0, max_deg = 0, nnz = 0, empty = 0;
   long long first_empty = LLONG_MAX, bad = LLONG_MAX;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t r = row0 + (int32_t)i;
-    const int64_t d = ptr[r + 1] - ptr[r];
+    const int64_t d = re[r] - rb[r];
     if (d < 0 || d > (int64_t)key_max) {
       bad = min(bad, (long long)r);
       keys[i] = key_max;
       vals[i] = r;
       continue;
     }
-    if (d == 0) first_empty = min(first_empty, (long long)r);
+    if (d == 0) {
+      first_empty = min(first_empty, (long long)r);
+      empty += 1;
+    }
     max_deg = max(max_deg, (long long)d);
+    nnz += d;
     if (d > light_max) {
       const long long nch = (d + chunk - 1) / chunk;
       heavy += 1;
@@ -66,6 +71,8 @@ __global__ void k_sched_keys(int32_t row0, int32_t rows, const int64_t* __restri
     heavy += __shfl_xor_sync(0xffffffffu, heavy, off);
     chunks += __shfl_xor_sync(0xffffffffu, chunks, off);
     partials += __shfl_xor_sync(0xffffffffu, partials, off);
+    nnz += __shfl_xor_sync(0xffffffffu, nnz, off);
+    empty += __shfl_xor_sync(0xffffffffu, empty, off);
     max_deg = max(max_deg, __shfl_xor_sync(0xffffffffu, max_deg, off));
     first_empty = min(first_empty, __shfl_xor_sync(0xffffffffu, first_empty, off));
     bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, off));
@@ -75,23 +82,22 @@ __global__ void k_sched_keys(int32_t row0, int32_t rows, const int64_t* __restri
     if (chunks) atomicAdd(reinterpret_cast<unsigned long long*>(stats + kChunks), (unsigned long long)chunks);
     if (partials)
       atomicAdd(reinterpret_cast<unsigned long long*>(stats + kPartials), (unsigned long long)partials);
+    if (nnz) atomicAdd(reinterpret_cast<unsigned long long*>(stats + kNnz), (unsigned long long)nnz);
+    if (empty) atomicAdd(reinterpret_cast<unsigned long long*>(stats + kEmpty), (unsigned long long)empty);
     if (max_deg) atomicMax(stats + kMaxDeg, max_deg);
     if (first_empty != LLONG_MAX) atomicMin(stats + kFirstEmpty, first_empty);
     if (bad != LLONG_MAX) atomicMin(stats + kBadRow, bad);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    stats[kNnz] = ptr[row0 + rows] - ptr[row0];
-    stats[kFirstPtr] = ptr[row0];
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats[kFirstPtr] = rb[row0];
 }
 
 __global__ void k_sched_light(int64_t n_light, const int32_t* __restrict__ sorted_rows,
-                              const int64_t* __restrict__ ptr, const float* __restrict__ invs,
-                              HgeLightItem* __restrict__ items) {
+                              const int64_t* __restrict__ rb, const int64_t* __restrict__ re,
+                              const float* __restrict__ invs, HgeLightItem* __restrict__ items) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_light;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t r = sorted_rows[i];
-    const int64_t b = ptr[r], d = ptr[r + 1] - b;
+    const int64_t b = rb[r], d = re[r] - b;
     HgeLightItem it;
     it.row = r;
     it.deg_hi = (uint32_t)d | (uint32_t)((b >> 32) << 8);
@@ -102,11 +108,12 @@ __global__ void k_sched_light(int64_t n_light, const int32_t* __restrict__ sorte
 }
 
 __global__ void k_sched_heavy_counts(int32_t n_heavy, const int32_t* __restrict__ sorted_rows,
-                                     const int64_t* __restrict__ ptr, int chunk,
+                                     const int64_t* __restrict__ rb,
+                                     const int64_t* __restrict__ re, int chunk,
                                      int32_t* __restrict__ nch, int32_t* __restrict__ npart) {
   for (int32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n_heavy; h += gridDim.x * blockDim.x) {
     const int32_t r = sorted_rows[h];
-    const int64_t d = ptr[r + 1] - ptr[r];
+    const int64_t d = re[r] - rb[r];
     const int32_t c = (int32_t)((d + chunk - 1) / chunk);
     nch[h] = c;
     npart[h] = c > 1 ? c : 0;
@@ -116,7 +123,8 @@ __global__ void k_sched_heavy_counts(int32_t n_heavy, const int32_t* __restrict_
 // One warp per long row: its descriptor and its (row, chunk) work items; the chunks of the
 // longest rows come first, so their reductions finish early.
 __global__ void k_sched_heavy_write(int32_t n_heavy, const int32_t* __restrict__ sorted_rows,
-                                    const int64_t* __restrict__ ptr, const float* __restrict__ invs,
+                                    const int64_t* __restrict__ rb, const int64_t* __restrict__ re,
+                                    const float* __restrict__ invs,
                                     int chunk, const int32_t* __restrict__ chunk_off,
                                     const int32_t* __restrict__ part_off,
                                     HgeHeavyRow* __restrict__ hrows, int2* __restrict__ chunks) {
@@ -124,7 +132,7 @@ __global__ void k_sched_heavy_write(int32_t n_heavy, const int32_t* __restrict__
   const int32_t warps = gridDim.x * (blockDim.x >> 5);
   for (int32_t h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < n_heavy; h += warps) {
     const int32_t r = sorted_rows[h];
-    const int64_t b = ptr[r], d = ptr[r + 1] - b;
+    const int64_t b = rb[r], d = re[r] - b;
     const int32_t nch = (int32_t)((d + chunk - 1) / chunk);
     if (lane == 0) {
       HgeHeavyRow hr;
@@ -151,11 +159,19 @@ int grid_for(const hge_ctx* ctx, int64_t work, int per_block) {
 
 int hge_sched_begin(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* d_ptr,
                     int64_t max_degree_possible, HgeHalfSchedule* s) {
+  return hge_sched_begin_ranges(ctx, row0, row1, d_ptr, d_ptr + 1, max_degree_possible, s);
+}
+
+int hge_sched_begin_ranges(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* row_begin,
+                           const int64_t* row_end, int64_t max_degree_possible,
+                           HgeHalfSchedule* s) {
   const int32_t rows = row1 - row0;
   s->rows = rows;
   s->row0 = row0;
   s->chunk_sz = ctx->chunk;
-  s->ptr = d_ptr;
+  s->ptr = row_begin;
+  s->row_end = row_end;
+  s->ranges = row_end != row_begin + 1;
   int bits = 1;
   while (bits < 31 && ((int64_t)1 << bits) <= max_degree_possible) ++bits;
   const uint32_t key_max = (uint32_t)(((int64_t)1 << bits) - 1);
@@ -172,7 +188,8 @@ int hge_sched_begin(hge_ctx* ctx, int32_t row0, int32_t row1, const int64_t* d_p
   k_sched_init<<<1, 32, 0, ctx->stream>>>(s->d_stats);
   HGE_CHECK_LAUNCH(ctx);
   k_sched_keys<<<grid_for(ctx, rows, kBlock), kBlock, 0, ctx->stream>>>(
-      row0, rows, d_ptr, ctx->light_max_deg, ctx->chunk, key_max, keys_in, vals_in, s->d_stats);
+      row0, rows, row_begin, row_end, ctx->light_max_deg, ctx->chunk, key_max, keys_in, vals_in,
+      s->d_stats);
   HGE_CHECK_LAUNCH(ctx);
   size_t temp_bytes = 0;
   HGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, vals_in,
@@ -201,7 +218,7 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
                   st[kBadRow]);
     return HGE_ERR_INVALID;
   }
-  if (s->row0 == 0 && st[kFirstPtr] != 0) {
+  if (s->row0 == 0 && !s->ranges && st[kFirstPtr] != 0) {
     hge_set_error("%s row pointers must start at 0", what);
     return HGE_ERR_INVALID;
   }
@@ -214,6 +231,9 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
   s->first_empty = st[kFirstEmpty] == LLONG_MAX ? -1 : (int32_t)st[kFirstEmpty];
   s->n_hrows = (int32_t)st[kHeavy];
   s->n_light = (int64_t)s->rows - s->n_hrows;
+  // rows are sorted by descending degree, so the empty ones are the tail of the light items; a
+  // tile of the edge half leaves them out (it adds nothing to their sums)
+  if (s->skip_empty) s->n_light -= st[kEmpty];
   s->n_chunks = (int32_t)st[kChunks];
   s->n_partials = (int32_t)st[kPartials];
   HGE_TRY(hge_dev_alloc(ctx, &s->light, (size_t)s->n_light));
@@ -221,7 +241,7 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
   HGE_TRY(hge_dev_alloc(ctx, &s->chunks, (size_t)s->n_chunks));
   if (s->n_light) {
     k_sched_light<<<grid_for(ctx, s->n_light, kBlock), kBlock, 0, ctx->stream>>>(
-        s->n_light, s->sorted_rows + s->n_hrows, s->ptr, s->invs, s->light);
+        s->n_light, s->sorted_rows + s->n_hrows, s->ptr, s->row_end, s->invs, s->light);
     HGE_CHECK_LAUNCH(ctx);
   }
   if (s->n_hrows) {
@@ -232,7 +252,7 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
     HGE_TRY(hge_dev_alloc(ctx, &coff, (size_t)nh));
     HGE_TRY(hge_dev_alloc(ctx, &poff, (size_t)nh));
     k_sched_heavy_counts<<<grid_for(ctx, nh, kBlock), kBlock, 0, ctx->stream>>>(
-        nh, s->sorted_rows, s->ptr, s->chunk_sz, nch, npart);
+        nh, s->sorted_rows, s->ptr, s->row_end, s->chunk_sz, nch, npart);
     HGE_CHECK_LAUNCH(ctx);
     size_t temp_bytes = 0;
     HGE_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, nch, coff, nh, ctx->stream));
@@ -242,7 +262,7 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
     HGE_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, npart, poff, nh, ctx->stream));
     ctx->launches += 2;
     k_sched_heavy_write<<<grid_for(ctx, nh, kBlock / 32), kBlock, 0, ctx->stream>>>(
-        nh, s->sorted_rows, s->ptr, s->invs, s->chunk_sz, coff, poff, s->hrows, s->chunks);
+        nh, s->sorted_rows, s->ptr, s->row_end, s->invs, s->chunk_sz, coff, poff, s->hrows, s->chunks);
     HGE_CHECK_LAUNCH(ctx);
     hge_dev_free(ctx, temp);
     hge_dev_free(ctx, nch);

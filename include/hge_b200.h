@@ -67,6 +67,16 @@ int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_pe
  * register gather of k_half_sweep.  Same results; measured slower for 128-byte rows
  * (profiles/r1_bulk_copy_experiment.md), so it is off by default. */
 int hge_ctx_set_bulk(hge_ctx* ctx, int enabled);
+/* Single-GPU edge half over node rows that exceed what random 128-byte gathers reach at full
+ * rate (measured on config 5: 1.9 TB/s over 8.3 GB of rows against ~6 TB/s inside 1 GB, i.e.
+ * TLB reach): when the node rows exceed min_rows_mb megabytes the half-sweep runs in node-range
+ * tiles of tile_mb megabytes of rows -- tile t gathers only the members of every edge that fall
+ * into its range (L2-resident at the default 64 MB) and adds their sum to an E x R buffer, one
+ * more pass finishes the rows.  Defaults 64 / 1024; tile_mb 0 disables.  Pays off when edges are
+ * large (config 5: 122 -> 37 ms per edge half); on many small edges the per-(edge, tile) cost
+ * dominates, hence the threshold.  Results differ from the untiled half-sweep only by fp32
+ * summation order. */
+int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hge_ctx_launch_count(const hge_ctx* ctx);
 

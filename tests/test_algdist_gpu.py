@@ -178,3 +178,29 @@ def test_config2_scale_properties(gpu_ctx):
   ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, 20)
   xn, xe = _run(A, xn0, xe0, 20, gpu_ctx)
   assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
+
+
+def test_node_range_tiles_of_the_edge_half(gpu_ctx):
+  """Single-GPU edge half in node-range tiles (hge_ctx_set_tile_mb): same result as the oracle
+  and, up to fp32 summation order, as the untiled half-sweep; deterministic."""
+  from hypergraphembedding_b200 import _native, synthetic
+  from hypergraphembedding_b200 import algebraic_distance as ad
+  from oracle import port
+  A = synthetic.power_law_hypergraph(60000, 900, 400000, seed=3, max_edge_size=30000)
+  R, iters = 32, 6
+  xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], R, seed=1)
+  want_n, want_e = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, iters)
+  results = []
+  try:
+    for tile_mb in (0, 1, 1, 2):
+      gpu_ctx.set_tile_mb(tile_mb, 0)      # 1 MB = 8192 rows of 32 floats -> 8 tiles
+      inc = ad.make_incidence(A, ctx=gpu_ctx)
+      xn, xe = xn0.copy(), xe0.copy()
+      ad.relax(inc, xn, xe, iters)
+      inc.close()
+      results.append((xn, xe))
+      assert np.abs(xn - want_n).max() < 2e-5 and np.abs(xe - want_e).max() < 2e-5, tile_mb
+  finally:
+    gpu_ctx.set_tile_mb(64, 1024)
+  assert np.array_equal(results[1][0], results[2][0]) and np.array_equal(results[1][1], results[2][1])
+  assert np.abs(results[0][1] - results[1][1]).max() < 5e-6
