@@ -143,6 +143,20 @@ __global__ void k_tile_offsets(int32_t rows, const int64_t* __restrict__ ptr,
   }
 }
 
+// Reduce-scatter of locally accumulated partial rows: row r goes to the staging block of its
+// owner (rank r / own_rows), slot `rank` (the push the gather kernel does itself when untiled).
+__global__ void k_push_rows(int32_t rows, int ld4, const float4* __restrict__ raw,
+                            float4* const* __restrict__ peer_stage, int32_t own_rows, int rank) {
+  const int64_t total = (int64_t)rows * ld4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = (int32_t)(i / ld4);
+    const int c4 = (int)(i - (int64_t)r * ld4);
+    const int owner = r / own_rows;
+    peer_stage[owner][((size_t)rank * own_rows + (r - owner * own_rows)) * ld4 + c4] = __ldcs(raw + i);
+  }
+}
+
 __global__ void k_fill_minmax(int32_t* mm, int slots, int ld) {
   const int n = slots * 2 * ld;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1177,8 +1191,9 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
   if ((rc = hge_dev_alloc(ctx, &st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
   if ((rc = hge_dev_alloc(ctx, &st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
     return fail(rc);
-  // single GPU, node rows far beyond what random gathers reach at full rate: tile the edge half
-  if (!inc->sharded && ctx->tile_mb > 0) {
+  // node rows far beyond what random gathers reach at full rate: tile the edge half (single
+  // GPU, and the peer-memory sweep of a shard; the NCCL path of a shard stays untiled)
+  if (ctx->tile_mb > 0) {
     const int64_t tile_rows64 = ((int64_t)ctx->tile_mb << 20) / ((int64_t)st->ld * 4);
     const int32_t tile_rows = (int32_t)std::max<int64_t>(1, std::min<int64_t>(tile_rows64, INT32_MAX));
     const int64_t row_bytes = (int64_t)inc->N * st->ld * 4;
@@ -1283,7 +1298,7 @@ int hge_algdist_node_half(hge_algdist* st, int sweep) {
 int hge_algdist_edge_half(hge_algdist* st, int sweep) {
   HGE_REQUIRE(st && sweep >= 0 && sweep < st->max_iters, "hge_algdist_edge_half: bad sweep %d", sweep);
   HGE_CUDA(cudaSetDevice(st->ctx->device));
-  if (!st->tile_raw) return run_half(st, false, sweep, nullptr);
+  if (!st->tile_raw || st->inc->sharded) return run_half(st, false, sweep, nullptr);
   // tiled: every tile adds the sums of its node range to tile_raw, then one pass blends,
   // rescales and stores the edge rows (the kernel the sharded path uses after its all-reduce)
   hge_ctx* ctx = st->ctx;
@@ -1331,7 +1346,19 @@ int hge_algdist_edge_finalize(hge_algdist* st, int sweep, int slice, const float
 }
 
 int hge_internal_edge_push(hge_algdist* st, int sweep) {
-  return run_half(st, false, sweep, nullptr, -1, st->p2p);
+  if (!st->tile_raw) return run_half(st, false, sweep, nullptr, -1, st->p2p);
+  // tiled: the local partial sums are accumulated tile by tile, then pushed to their owners
+  hge_ctx* ctx = st->ctx;
+  hge_incidence* inc = st->inc;
+  const hge_p2p* p = st->p2p;
+  HGE_CUDA(cudaMemsetAsync(st->tile_raw, 0, (size_t)inc->E * st->ld * sizeof(float), ctx->stream));
+  for (size_t t = 0; t < inc->edge_tiles.size(); ++t)
+    HGE_TRY(run_half(st, false, sweep, st->tile_raw, -1, nullptr, &inc->edge_tiles[t], true));
+  k_push_rows<<<grid_1d(ctx, (int64_t)inc->E * st->ld4, kBlock), kBlock, 0, ctx->stream>>>(
+      inc->E, st->ld4, reinterpret_cast<const float4*>(st->tile_raw), p->d_peer_stage, p->own_rows,
+      p->rank);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
 }
 
 int hge_algdist_minmax_ptr(hge_algdist* st, int sweep, int32_t** out) {
