@@ -92,6 +92,9 @@ SIGNATURES = {
                                    c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int]),
     "hge_scale_transform": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_double, c_vp,
                                            ctypes.c_int]),
+    "hge_scale_minmax": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int]),
+    "hge_scale_apply": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_double, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_int]),
     "hge_row_span": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp,
                                     ctypes.c_int]),
     "hge_same_type_prob": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp,
@@ -470,6 +473,19 @@ def scale_transform(ctx, values, alpha, want_minmax=False):
   check(ctx.lib.hge_scale_transform(ctx.handle, ptr(values), int(values.shape[0]), float(alpha),
                                     ptr(mm), _mem(values)), "hge_scale_transform")
   return (values, mm) if want_minmax else values
+
+
+def scale_minmax(ctx, values):
+  mm = np.zeros(2, dtype=np.float32)
+  check(ctx.lib.hge_scale_minmax(ctx.handle, ptr(values), int(values.shape[0]), ptr(mm), _mem(values)),
+        "hge_scale_minmax")
+  return float(mm[0]), float(mm[1])
+
+
+def scale_apply(ctx, values, alpha, lo, hi):
+  check(ctx.lib.hge_scale_apply(ctx.handle, ptr(values), int(values.shape[0]), float(alpha), float(lo),
+                                float(hi), _mem(values)), "hge_scale_apply")
+  return values
 
 
 def row_span(ctx, inc, xn, xe, side):

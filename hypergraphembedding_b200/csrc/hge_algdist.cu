@@ -143,6 +143,18 @@ __global__ void k_tile_offsets(int32_t rows, const int64_t* __restrict__ ptr,
   }
 }
 
+// Number of (row, tile) pairs with at least one incidence (how much per-pair work tiling adds).
+__global__ void k_count_tile_pairs(int64_t total, int32_t rows, const int64_t* __restrict__ pos,
+                                   unsigned long long* count) {
+  unsigned long long c = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x)
+    c += pos[i + rows] > pos[i];
+#pragma unroll
+  for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(kFull, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 // Reduce-scatter of locally accumulated partial rows: row r goes to the staging block of its
 // owner (rank r / own_rows), slot `rank` (the push the gather kernel does itself when untiled).
 __global__ void k_push_rows(int32_t rows, int ld4, const float4* __restrict__ raw,
@@ -1137,6 +1149,30 @@ static int ensure_edge_tiles(hge_ctx* ctx, hge_incidence* inc, int32_t tile_rows
   k_tile_offsets<<<grid_1d(ctx, (int64_t)inc->E * (tiles + 1), kBlock), kBlock, 0, ctx->stream>>>(
       inc->E, inc->e2n_ptr, inc->e2n_idx, tiles, tile_rows, inc->tile_pos);
   HGE_CHECK_LAUNCH(ctx);
+  // Tiling adds work per non-empty (edge, tile) pair (a work item, a read-modify-write of the
+  // partial row): it pays when edges are large (config 5: ~180 incidences per pair) and costs
+  // more than it saves when they are small (config 2 forced into tiles: ~7 per pair, edge half
+  // 0.24 -> 0.45 ms).  Below kMinPerPair incidences per pair the half-sweep stays untiled.
+  {
+    constexpr double kMinPerPair = 16.0;
+    unsigned long long* d_pairs = nullptr;
+    HGE_TRY(hge_dev_alloc(ctx, &d_pairs, 1));
+    HGE_CUDA(cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), ctx->stream));
+    k_count_tile_pairs<<<grid_1d(ctx, (int64_t)inc->E * tiles, kBlock), kBlock, 0, ctx->stream>>>(
+        (int64_t)inc->E * tiles, inc->E, inc->tile_pos, d_pairs);
+    HGE_CHECK_LAUNCH(ctx);
+    unsigned long long* h_pairs = static_cast<unsigned long long*>(hge_ctx_pinned_slot(ctx));
+    if (!h_pairs) return HGE_ERR_NOMEM;
+    HGE_CUDA(cudaMemcpyAsync(h_pairs, d_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+    hge_dev_free(ctx, d_pairs);
+    const double per_pair = *h_pairs ? (double)eh.nnz / (double)*h_pairs : 0.0;
+    if (per_pair < kMinPerPair && !ctx->tile_force) {
+      hge_dev_free(ctx, inc->tile_pos);
+      return HGE_OK;
+    }
+  }
   inc->edge_tiles.resize((size_t)tiles);
   for (int t = 0; t < tiles; ++t) {
     inc->edge_tiles[(size_t)t].skip_empty = true;

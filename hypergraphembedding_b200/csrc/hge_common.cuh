@@ -53,6 +53,7 @@ struct hge_ctx {
   int use_bulk;          // long rows through the bulk-copy engine (k_heavy_bulk)
   int tile_mb;           // node-range tile of the single-GPU edge half in MB of rows (0 = off)
   int tile_min_mb;       // ... used when the node rows exceed this many MB
+  int tile_force;        // min_rows_mb == 0 (tests): tile whatever the edge sizes are
   int64_t launches;
   // ring of 128-byte pinned host slots for small device -> host read-backs (schedule statistics)
   char* pinned_ring;

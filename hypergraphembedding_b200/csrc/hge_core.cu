@@ -95,12 +95,13 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->use_bulk = 0;
   if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;
   // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
-  // the single-GPU edge half over more than 1 GB of node rows is tiled by node range into
-  // L2-sized tiles (profiles/r1_tiled_edge_half.md)
+  // the edge half over more than 512 MB of node rows is tiled by node range into L2-sized tiles
+  // when the edges are large enough for that to pay (profiles/r1_tiled_edge_half.md)
   ctx->tile_mb = 64;
-  ctx->tile_min_mb = 1024;
+  ctx->tile_min_mb = 512;
   if (const char* env = getenv("HGE_TILE_MB")) ctx->tile_mb = atoi(env);
   if (const char* env = getenv("HGE_TILE_MIN_MB")) ctx->tile_min_mb = atoi(env);
+  ctx->tile_force = ctx->tile_min_mb == 0;
   ctx->launches = 0;
   ctx->pinned_ring = nullptr;
   ctx->pinned_next = 0;
@@ -179,6 +180,7 @@ int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb) {
               "hge_ctx_set_tile_mb: %d / %d MB not in [0, 2^20]", tile_mb, min_rows_mb);
   ctx->tile_mb = tile_mb;
   ctx->tile_min_mb = min_rows_mb;
+  ctx->tile_force = min_rows_mb == 0;
   return HGE_OK;
 }
 

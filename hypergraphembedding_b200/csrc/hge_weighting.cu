@@ -515,6 +515,64 @@ int hge_scale_transform(hge_ctx* ctx, float* values, int64_t n, double alpha, fl
   return s_v.finish();
 }
 
+// The two halves of hge_scale_transform for values that are spread over several GPUs: every rank
+// reduces its own values, the caller all-reduces (min, max) over the ranks, every rank applies.
+int hge_scale_minmax(hge_ctx* ctx, const float* values, int64_t n, float* minmax, int mem) {
+  HGE_REQUIRE(ctx && minmax && (values || n == 0) && n >= 0, "hge_scale_minmax: bad argument");
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  minmax[0] = INFINITY;
+  minmax[1] = -INFINITY;
+  if (n == 0) return HGE_OK;
+  Staged<float> s_v;
+  HGE_TRY(s_v.init(ctx, values, (size_t)n, mem, true, false));
+  int32_t* mm = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &mm, 2));
+  k_minmax_init<<<1, 1, 0, ctx->stream>>>(mm);
+  ctx->launches++;
+  k_minmax<<<grid_for(ctx, n, kBlock * 8), kBlock, 0, ctx->stream>>>(n, s_v.dev, mm);
+  ctx->launches++;
+  int32_t h[2];
+  cudaError_t e = cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  hge_dev_free(ctx, mm);
+  if (e != cudaSuccess) {
+    hge_set_error("hge_scale_minmax: %s", cudaGetErrorString(e));
+    return HGE_ERR_CUDA;
+  }
+  minmax[0] = hge_dec(h[0]);
+  minmax[1] = hge_dec(h[1]);
+  return HGE_OK;
+}
+
+int hge_scale_apply(hge_ctx* ctx, float* values, int64_t n, double alpha, float lo, float hi,
+                    int mem) {
+  HGE_REQUIRE(ctx && (values || n == 0) && n >= 0, "hge_scale_apply: bad argument");
+  HGE_REQUIRE(alpha >= 0.0 && alpha <= 1.0, "hge_scale_apply: alpha %g not in [0, 1] "
+              "(hg2v_weighting.py:331-332)", alpha);
+  HGE_REQUIRE(lo <= hi, "hge_scale_apply: min %g > max %g", lo, hi);
+  if (n == 0) return HGE_OK;
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  Staged<float> s_v;
+  HGE_TRY(s_v.init(ctx, values, (size_t)n, mem, true, true));
+  int32_t* mm = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &mm, 2));
+  const int32_t h[2] = {hge_enc(lo), hge_enc(hi)};
+  cudaError_t e = cudaMemcpyAsync(mm, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    k_scale_transform<<<grid_for(ctx, n, kBlock * 8), kBlock, 0, ctx->stream>>>(
+        n, s_v.dev, mm, (float)alpha, (float)(1.0 - alpha));
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // h is on this stack frame
+  hge_dev_free(ctx, mm);
+  if (e != cudaSuccess) {
+    hge_set_error("hge_scale_apply: %s", cudaGetErrorString(e));
+    return HGE_ERR_CUDA;
+  }
+  return s_v.finish();
+}
+
 int hge_row_span(hge_ctx* ctx, hge_incidence* inc, const float* xn, const float* xe, int R,
                  int side, float* span, int mem) {
   HGE_REQUIRE(ctx && inc && xn && xe && span, "hge_row_span: NULL argument");

@@ -297,3 +297,39 @@ class ShardedRelaxation(object):
 
   def close(self):
     self.ops.close()
+
+
+def sharded_pair_weights(xa, xb, ia_local, ib_local, alpha, group=None, ctx=None, ops=None):
+  """Distance weights alpha + (1 - alpha) * (1 - zero_one(||xa[i] - xb[j]||)) of pairs that are
+  sharded over the ranks (embarrassingly parallel over the pairs once the
+  vectors are replicated).  Every rank passes its own slice of the pair list and the full,
+  identical vector blocks; the only exchange is the all-reduce of (min, max) of the distances,
+  so the weights equal those of one call over the concatenated list
+  (hg2v_weighting.py:40-45, 94-95).  Returns this rank's weights."""
+  import torch
+  import torch.distributed as dist
+  ops = ops or _NativePairOps(ctx or _native.default_context())
+  d = ops.pair_l2(xa, xb, ia_local, ib_local)
+  lo, hi = ops.minmax(d)
+  mm = torch.tensor([lo, -hi], dtype=torch.float64)
+  if dist.get_backend(group) == "nccl":
+    mm = mm.cuda()
+  dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
+  lo, hi = float(mm[0]), -float(mm[1])
+  if not lo <= hi:       # no pair anywhere
+    return d
+  return ops.apply(d, alpha, lo, hi)
+
+
+class _NativePairOps(object):
+  def __init__(self, ctx):
+    self.ctx = ctx
+
+  def pair_l2(self, xa, xb, ia, ib):
+    return _native.pair_l2(self.ctx, xa, xb, ia, ib)
+
+  def minmax(self, d):
+    return _native.scale_minmax(self.ctx, d)
+
+  def apply(self, d, alpha, lo, hi):
+    return _native.scale_apply(self.ctx, d, alpha, lo, hi)

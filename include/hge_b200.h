@@ -67,15 +67,17 @@ int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_pe
  * register gather of k_half_sweep.  Same results; measured slower for 128-byte rows
  * (profiles/r1_bulk_copy_experiment.md), so it is off by default. */
 int hge_ctx_set_bulk(hge_ctx* ctx, int enabled);
-/* Single-GPU edge half over node rows that exceed what random 128-byte gathers reach at full
- * rate (measured on config 5: 1.9 TB/s over 8.3 GB of rows against ~6 TB/s inside 1 GB, i.e.
- * TLB reach): when the node rows exceed min_rows_mb megabytes the half-sweep runs in node-range
- * tiles of tile_mb megabytes of rows -- tile t gathers only the members of every edge that fall
- * into its range (L2-resident at the default 64 MB) and adds their sum to an E x R buffer, one
- * more pass finishes the rows.  Defaults 64 / 1024; tile_mb 0 disables.  Pays off when edges are
- * large (config 5: 122 -> 37 ms per edge half); on many small edges the per-(edge, tile) cost
- * dominates, hence the threshold.  Results differ from the untiled half-sweep only by fp32
- * summation order. */
+/* Edge half over node rows that exceed what random 128-byte gathers reach at full rate
+ * (measured on config 5: 1.9 TB/s over 8.3 GB of rows, 4.9 TB/s inside 1 GB, 6.3 TB/s inside an
+ * L2-sized block): when the (local) node rows exceed min_rows_mb megabytes the half-sweep runs
+ * in node-range tiles of tile_mb megabytes of rows -- tile t gathers only the members of every
+ * edge that fall into its range and adds their sum to an E x R buffer, one more pass finishes
+ * the rows (single GPU) or pushes them to their owners (peer-memory sweep of a shard).
+ * Defaults 64 / 512; tile_mb 0 disables; min_rows_mb 0 forces tiles even when the edges are too
+ * small for them to pay (< 16 incidences per non-empty (edge, tile) pair, where the per-pair
+ * work dominates and the half-sweep otherwise stays untiled).  Config 5: 122 -> 37 ms per edge
+ * half on one GPU, 200 -> 159 ms per step on 8.  Results differ from the untiled half-sweep only
+ * by fp32 summation order. */
 int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hge_ctx_launch_count(const hge_ctx* ctx);
@@ -190,6 +192,13 @@ int hge_pair_l2(hge_ctx* ctx, const float* xa, int64_t rows_a, const float* xb, 
  * host, 2 floats) receives (min, max).  alpha outside [0, 1] is HGE_ERR_INVALID. */
 int hge_scale_transform(hge_ctx* ctx, float* values, int64_t n, double alpha, float* minmax,
                         int mem);
+
+/* The same transform in two steps, for values spread over several GPUs (pairs are sharded over
+ * the ranks): each rank reduces its own values to (min, max), the caller
+ * all-reduces them (MIN / MAX), each rank applies the transform with the global pair. */
+int hge_scale_minmax(hge_ctx* ctx, const float* values, int64_t n, float* minmax, int mem);
+int hge_scale_apply(hge_ctx* ctx, float* values, int64_t n, double alpha, float lo, float hi,
+                    int mem);
 
 /* span[r] = max(0, max over neighbours b and components c of (x_other[b][c] - x_self[r][c]))
  *         - min(0, min over the same set), for the rows of the node->edge CSR (side == 0,

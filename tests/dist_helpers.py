@@ -157,3 +157,46 @@ def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, us
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), xn=xn, xe=xe, r0=r0, r1=r1)
   finally:
     dist.destroy_process_group()
+
+
+class NumpyPairOps(object):
+  """numpy stand-in for the pair-distance kernels behind distributed.sharded_pair_weights."""
+
+  def pair_l2(self, xa, xb, ia, ib):
+    d = np.asarray(xa, np.float64)[ia] - np.asarray(xb, np.float64)[ib]
+    return np.sqrt((d * d).sum(1)).astype(np.float32)
+
+  def minmax(self, d):
+    return (float(d.min()), float(d.max())) if len(d) else (float("inf"), float("-inf"))
+
+  def apply(self, d, alpha, lo, hi):
+    d = np.asarray(d, dtype=np.float32)
+    span = np.float32(hi) - np.float32(lo)
+    scaled = np.ones_like(d) if span == 0 else (d - np.float32(lo)) / span
+    return (np.float32(alpha) + np.float32(1 - alpha) * (np.float32(1) - scaled)).astype(np.float32)
+
+
+def pair_worker(rank, world, port, backend, seed, num_pairs, alpha, out_dir, use_native):
+  """Weights of this rank's slice of a pair list (distributed.sharded_pair_weights)."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import distributed as hd
+  if use_native:
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+  dist.init_process_group(backend=backend, rank=rank, world_size=world)
+  try:
+    rng = np.random.default_rng(seed)
+    xa = rng.random((500, 12)).astype(np.float32)
+    xb = rng.random((300, 12)).astype(np.float32)
+    ia = rng.integers(0, 500, num_pairs).astype(np.int32)
+    ib = rng.integers(0, 300, num_pairs).astype(np.int32)
+    lo, hi = num_pairs * rank // world, num_pairs * (rank + 1) // world
+    if rank == world - 1 and world > 1:
+      lo = hi                                    # one rank without pairs must not break the bounds
+    w = hd.sharded_pair_weights(xa, xb, ia[lo:hi], ib[lo:hi], alpha,
+                                ops=None if use_native else NumpyPairOps())
+    np.savez(os.path.join(out_dir, "pairs%d.npz" % rank), w=np.asarray(w), lo=lo, hi=hi)
+  finally:
+    dist.destroy_process_group()

@@ -53,3 +53,25 @@ def test_two_rank_relaxation_matches_single_process_oracle(tmp_path, world, slic
     got_xn[int(z["r0"]):int(z["r1"])] = z["xn"]
     assert np.abs(z["xe"] - ref_xe).max() < 2e-6        # replicated edge block, every rank
   assert np.abs(got_xn - ref_xn).max() < 2e-6
+
+
+def test_sharded_pair_weights_share_one_min_max(tmp_path):
+  """Pairs sharded over 2 ranks (one of them empty-handed): the weights equal the single-process
+  transform over the pairs that were weighted, because (min, max) are all-reduced."""
+  world, num_pairs, alpha = 2, 4000, 0.25
+  mp.spawn(dist_helpers.pair_worker,
+           args=(world, _free_port(), "gloo", 5, num_pairs, alpha, str(tmp_path), False),
+           nprocs=world, join=True)
+  rng = np.random.default_rng(5)
+  xa = rng.random((500, 12)).astype(np.float32)
+  xb = rng.random((300, 12)).astype(np.float32)
+  ia = rng.integers(0, 500, num_pairs).astype(np.int32)
+  ib = rng.integers(0, 300, num_pairs).astype(np.int32)
+  parts = [np.load(tmp_path / ("pairs%d.npz" % r)) for r in range(world)]
+  done = np.concatenate([np.arange(int(z["lo"]), int(z["hi"])) for z in parts])
+  got = np.concatenate([z["w"] for z in parts])
+  dist64 = np.sqrt(((xa.astype(np.float64)[ia[done]] - xb.astype(np.float64)[ib[done]])**2).sum(1))
+  want = alpha + (1 - alpha) * (1 - (dist64 - dist64.min()) / (dist64.max() - dist64.min()))
+  assert len(got) == len(done) == num_pairs // 2 and len(parts[1]["w"]) == 0
+  assert np.abs(got - want).max() < 1e-5
+  assert got.min() >= alpha - 1e-6 and abs(got.max() - 1.0) < 1e-6

@@ -172,3 +172,31 @@ def test_device_resident_pair_weighting(gpu_ctx):
   lo, hi = want.min(), want.max()
   want_w = 0.1 + 0.9 * (1 - (want - lo) / (hi - lo))
   assert np.allclose(d.cpu().numpy(), want_w, rtol=RTOL, atol=2e-6)
+
+
+def test_two_step_scale_transform_equals_the_fused_one(gpu_ctx):
+  """hge_scale_minmax + hge_scale_apply (the sharded form) give the bits of
+  hge_scale_transform; the sharded pair weighting on one rank equals pair_l2 + scale_transform."""
+  import socket
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import _native
+  from hypergraphembedding_b200 import distributed as hd
+  rng = np.random.default_rng(4)
+  v = (rng.random(100000) * 7).astype(np.float32)
+  fused = _native.scale_transform(gpu_ctx, v.copy(), 0.3)
+  lo, hi = _native.scale_minmax(gpu_ctx, v)
+  assert (lo, hi) == (float(v.min()), float(v.max()))
+  assert np.array_equal(_native.scale_apply(gpu_ctx, v.copy(), 0.3, lo, hi), fused)
+  xa, xb = rng.random((400, 20)).astype(np.float32), rng.random((90, 20)).astype(np.float32)
+  ia, ib = rng.integers(0, 400, 5000).astype(np.int32), rng.integers(0, 90, 5000).astype(np.int32)
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port_no = s.getsockname()[1]
+  s.close()
+  dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port_no, rank=0, world_size=1)
+  try:
+    got = hd.sharded_pair_weights(xa, xb, ia, ib, 0.1, ctx=gpu_ctx)
+  finally:
+    dist.destroy_process_group()
+  want = _native.scale_transform(gpu_ctx, _native.pair_l2(gpu_ctx, xa, xb, ia, ib), 0.1)
+  assert np.array_equal(got, want)
