@@ -275,10 +275,10 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
                         uint32_t* state625, int32_t* out_row, int32_t* out_col, int64_t capacity,
                         int64_t* out_count);
 
-/* Worker threads that build candidate rows ahead of the (sequential) draw loop of
- * hge_sample_adj_rows: 0 = automatic (inline below 512 product rows, up to 4 threads below 16K
- * rows, up to 16 above; HGE_SAMPLER_THREADS overrides), 1 = build rows inline.  Results do not
- * depend on it. */
+/* Worker threads around the (sequential) draw loop of hge_sample_adj_rows: they build the
+ * candidate rows ahead of it and turn its draws into samples behind it.  0 = automatic (inline
+ * below 512 product rows, else up to 4 workers; HGE_SAMPLER_THREADS overrides), 1 = everything
+ * inline.  Results do not depend on it. */
 int hge_sampler_set_threads(int threads);
 
 /* _sample_neighbors (hg2v_sample.py:49-51) for a list of (node, edge) samples: per sample k
