@@ -153,7 +153,7 @@ class ClockSampler(object):
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
           stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -499,11 +499,13 @@ def run_ours(args, spec):
     xe.copy_(xe_init)
     _native.algdist_run(ctx, inc, xn, xe, sweeps)
 
+  # clocks / throttle reasons are sampled from the warm-up to the end of the per-launch timing
+  # pass below, so that the short timed region (~0.1 s) is inside a longer window under load
+  sampler = ClockSampler(local_rank)
+  sampler.start()
   for _ in range(args.warmup):
     step_device()
   torch.cuda.synchronize()
-  sampler = ClockSampler(local_rank)
-  sampler.start()
   launches0 = ctx.launch_count
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   torch.cuda.synchronize()
@@ -514,7 +516,6 @@ def run_ours(args, spec):
   torch.cuda.synchronize()
   total_ms = ev0.elapsed_time(ev1)
   launches = ctx.launch_count - launches0
-  clocks = sampler.stop()
   ms_per_step = total_ms / args.steps
   value = nnz * R * sweeps / (ms_per_step * 1e-3)
 
@@ -536,6 +537,7 @@ def run_ours(args, spec):
     half_ms.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(2 * sweeps))
   st.store(sweeps, xn, xe)
   st.close()
+  clocks = sampler.stop()
   half_ms = np.asarray(half_ms)
   node_ms = float(half_ms[0::2].mean())
   edge_ms = float(half_ms[1::2].mean())

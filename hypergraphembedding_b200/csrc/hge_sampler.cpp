@@ -395,6 +395,22 @@ class SamplePipeline {
 
 std::atomic<int> g_sampler_threads{0};   // 0 = automatic
 
+// fn(lo, hi) over [0, n) in contiguous slices, on up to 4 threads when there is enough to do
+template <typename F>
+void parallel_for(int64_t n, F fn) {
+  int threads = g_sampler_threads.load();
+  if (threads == 0) threads = (int)std::min<unsigned>(4u, std::max(1u, std::thread::hardware_concurrency()));
+  if (n < 65536 || threads <= 1) {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t)
+    pool.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+  fn(0, n / threads);
+  for (std::thread& th : pool) th.join();
+}
+
 int sampler_threads_for(int kind, int64_t num_rows) {
   int n = g_sampler_threads.load();
   if (n == 0) {
@@ -593,23 +609,52 @@ int hge_sample_neighbors(const int64_t* n2e_ptr, const int32_t* n2e_idx, const i
               "hge_sample_neighbors: NULL output");
   HGE_REQUIRE(state625[624] <= 624, "hge_sample_neighbors: RNG pos %u out of range", state625[624]);
   StateGuard g(state625);
-  std::vector<uint32_t> draws((size_t)std::max(k, 1));
-  for (int64_t s = 0; s < num_samples; ++s) {
-    // edges of the node first, then nodes of the edge (hg2v_sample.py:184-187, 604-605)
-    const int64_t nb = n2e_ptr[nodes[s]], nd = n2e_ptr[nodes[s] + 1] - nb;
-    const int64_t eb = e2n_ptr[edges[s]], ed = e2n_ptr[edges[s] + 1] - eb;
-    if (k > 0 && (nd == 0 || ed == 0)) {
-      hge_set_error("hge_sample_neighbors: sample %lld has no neighbours to draw from "
-                    "(numpy: 'a' cannot be empty unless no samples are taken)", (long long)s);
-      return HGE_ERR_INVALID;
+  if (k == 0 || num_samples == 0) return HGE_OK;
+  // Three passes, only the middle one sequential: (1) degrees and row starts of every sample's
+  // node and edge (random reads of the row pointers, in parallel); (2) the draws, k per side,
+  // edges of the node first, then nodes of the edge (hg2v_sample.py:184-187, 604-605), streaming
+  // through the arrays of pass 1; (3) draws -> neighbour ids (random reads of the column ids, in
+  // parallel).  The draws are parked in the output arrays.
+  std::vector<int64_t> base((size_t)num_samples * 2);
+  std::vector<uint32_t> bound((size_t)num_samples * 2);
+  std::atomic<int64_t> empty_sample{-1};
+  parallel_for(num_samples, [&](int64_t lo, int64_t hi) {
+    for (int64_t s = lo; s < hi; ++s) {
+      const int64_t nb = n2e_ptr[nodes[s]], nd = n2e_ptr[nodes[s] + 1] - nb;
+      const int64_t eb = e2n_ptr[edges[s]], ed = e2n_ptr[edges[s] + 1] - eb;
+      if (nd <= 0 || ed <= 0) {
+        int64_t seen = empty_sample.load();
+        while ((seen < 0 || s < seen) && !empty_sample.compare_exchange_weak(seen, s)) {
+        }
+      }
+      base[(size_t)s * 2] = nb;
+      base[(size_t)s * 2 + 1] = eb;
+      bound[(size_t)s * 2] = (uint32_t)std::max<int64_t>(nd - 1, 0);
+      bound[(size_t)s * 2 + 1] = (uint32_t)std::max<int64_t>(ed - 1, 0);
     }
-    if (k > 0) {
-      g.mt.interval_many((uint32_t)(nd - 1), k, draws.data());
-      for (int t = 0; t < k; ++t) out_nbr_edges[s * k + t] = n2e_idx[nb + draws[(size_t)t]];
-      g.mt.interval_many((uint32_t)(ed - 1), k, draws.data());
-      for (int t = 0; t < k; ++t) out_nbr_nodes[s * k + t] = e2n_idx[eb + draws[(size_t)t]];
-    }
+  });
+  if (empty_sample.load() >= 0) {
+    hge_set_error("hge_sample_neighbors: sample %lld has no neighbours to draw from "
+                  "(numpy: 'a' cannot be empty unless no samples are taken)",
+                  (long long)empty_sample.load());
+    return HGE_ERR_INVALID;
   }
+  uint32_t* draw_e = reinterpret_cast<uint32_t*>(out_nbr_edges);
+  uint32_t* draw_n = reinterpret_cast<uint32_t*>(out_nbr_nodes);
+  for (int64_t s = 0; s < num_samples; ++s) {
+    g.mt.interval_many(bound[(size_t)s * 2], k, draw_e + s * k);
+    g.mt.interval_many(bound[(size_t)s * 2 + 1], k, draw_n + s * k);
+  }
+  parallel_for(num_samples, [&](int64_t lo, int64_t hi) {
+    for (int64_t s = lo; s < hi; ++s) {
+      const int32_t* row_e = n2e_idx + base[(size_t)s * 2];
+      const int32_t* row_n = e2n_idx + base[(size_t)s * 2 + 1];
+      for (int t = 0; t < k; ++t) {
+        out_nbr_edges[s * k + t] = row_e[draw_e[s * k + t]];
+        out_nbr_nodes[s * k + t] = row_n[draw_n[s * k + t]];
+      }
+    }
+  });
   return HGE_OK;
 }
 
