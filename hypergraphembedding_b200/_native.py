@@ -60,6 +60,8 @@ SIGNATURES = {
     "hge_incidence_nnz": (ctypes.c_int64, [c_vp]),
     "hge_algdist_run": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, c_vp]),
+    "hge_column_rescale": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.c_int]),
     "hge_algdist_create": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(c_vp)]),
     "hge_algdist_destroy": (ctypes.c_int, [c_vp]),

@@ -37,6 +37,46 @@ def make_incidence(n2e_csr, e2n_csr=None, ctx=None):
   return _native.Incidence(ctx, n2e_csr.shape[0], n2e_csr.shape[1], a_ptr, a_idx, b_ptr, b_idx)
 
 
+def _helper_update_embeddings(hypergraph, node_embeddings, edge_embeddings, node2edges, edge2nodes,
+                              workers=None, disable_pbar=True):
+  """algebraic_distance.py:54-91: one un-rescaled sweep -- nodes placed with respect to the old
+  edge vectors, then edges with respect to the new node vectors.  Returns new arrays."""
+  del hypergraph, workers, disable_pbar
+  ctx = _native.default_context()
+  a_ptr, a_idx = csr_arrays(node2edges)
+  b_ptr, b_idx = csr_arrays(edge2nodes)
+  xn = np.ascontiguousarray(node_embeddings, dtype=np.float32).copy()
+  xe = np.ascontiguousarray(edge_embeddings, dtype=np.float32).copy()
+  inc = _native.Incidence(ctx, xn.shape[0], xe.shape[0], a_ptr, a_idx, b_ptr, b_idx)
+  try:
+    state = _native.AlgDistState(ctx, inc, xn.shape[1], 1)
+    try:
+      state.load(xn, xe)
+      state.node_half(0)
+      state.edge_half(0)
+      state.store(0, xn, xe)       # sweeps_done = 0: no rescale applied
+    finally:
+      state.close()
+  finally:
+    inc.close()
+  return xn, xe
+
+
+def _helper_scale_embeddings(hypergraph, node_embeddings, edge_embeddings, workers=None,
+                             disable_pbar=True):
+  """algebraic_distance.py:97-123: joint per-column min-max rescale to the unit hypercube, in
+  place on fp32 arrays (a copy is returned for other dtypes)."""
+  del hypergraph, workers, disable_pbar
+  ctx = _native.default_context()
+  xn = np.ascontiguousarray(node_embeddings, dtype=np.float32)
+  xe = np.ascontiguousarray(edge_embeddings, dtype=np.float32)
+  assert xn.shape[1] == xe.shape[1]
+  _native.check(ctx.lib.hge_column_rescale(ctx.handle, _native.ptr(xn), xn.shape[0], _native.ptr(xe),
+                                           xe.shape[0], xn.shape[1], _native.MEM_HOST),
+                "hge_column_rescale")
+  return xn, xe
+
+
 def EmbedAlgebraicDistance(hypergraph,
                            dimension,
                            iterations=20,

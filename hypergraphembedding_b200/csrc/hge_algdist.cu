@@ -169,6 +169,29 @@ __global__ void k_push_rows(int32_t rows, int ld4, const float4* __restrict__ ra
   }
 }
 
+// Stand-alone joint rescale (_helper_scale_embeddings, algebraic_distance.py:97-123) of dense
+// [rows, R] blocks: per-column min / max over both blocks, then x <- (x - min) / (max - min).
+__global__ void k_dense_minmax(int64_t rows, int R, const float* __restrict__ x, int32_t* mm) {
+  const int64_t total = rows * R;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % R);
+    const int v = hge_enc(x[i]);
+    atomicMin(mm + c, v);
+    atomicMax(mm + R + c, v);
+  }
+}
+__global__ void k_dense_rescale(int64_t rows, int R, float* __restrict__ x,
+                                const int32_t* __restrict__ mm) {
+  const int64_t total = rows * R;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % R);
+    const float lo = hge_dec(mm[c]), hi = hge_dec(mm[R + c]);
+    x[i] = (x[i] - lo) / (hi - lo);
+  }
+}
+
 __global__ void k_fill_minmax(int32_t* mm, int slots, int ld) {
   const int n = slots * 2 * ld;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1428,6 +1451,45 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
   if (mem == HGE_MEM_HOST) {
     HGE_CUDA(cudaMemcpyAsync(xn, dn, (size_t)inc->N * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
     HGE_CUDA(cudaMemcpyAsync(xe, de, (size_t)inc->E * st->R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaEventRecord(ctx->stage_idle, ctx->stream));
+    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return HGE_OK;
+}
+
+int hge_column_rescale(hge_ctx* ctx, float* xn, int64_t num_nodes, float* xe, int64_t num_edges,
+                       int R, int mem) {
+  HGE_REQUIRE(ctx && xn && xe && num_nodes >= 0 && num_edges >= 0 && R >= 1,
+              "hge_column_rescale: bad argument");
+  HGE_REQUIRE(mem == HGE_MEM_HOST || mem == HGE_MEM_DEVICE, "hge_column_rescale: bad mem %d", mem);
+  HGE_CUDA(cudaSetDevice(ctx->device));
+  float* dn = xn;
+  float* de = xe;
+  const size_t nn = (size_t)num_nodes * R, ne = (size_t)num_edges * R;
+  if (mem == HGE_MEM_HOST) {
+    float* stage = nullptr;
+    HGE_TRY(hge_ctx_stage(ctx, nn + ne, &stage));
+    dn = stage;
+    de = stage + nn;
+    HGE_CUDA(cudaMemcpyAsync(dn, xn, nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HGE_CUDA(cudaMemcpyAsync(de, xe, ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int32_t* mm = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &mm, (size_t)2 * R));
+  k_fill_minmax<<<grid_1d(ctx, 2 * R, kBlock), kBlock, 0, ctx->stream>>>(mm, 1, R);
+  HGE_CHECK_LAUNCH(ctx);
+  k_dense_minmax<<<grid_1d(ctx, (int64_t)nn, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, R, dn, mm);
+  HGE_CHECK_LAUNCH(ctx);
+  k_dense_minmax<<<grid_1d(ctx, (int64_t)ne, kBlock), kBlock, 0, ctx->stream>>>(num_edges, R, de, mm);
+  HGE_CHECK_LAUNCH(ctx);
+  k_dense_rescale<<<grid_1d(ctx, (int64_t)nn, kBlock), kBlock, 0, ctx->stream>>>(num_nodes, R, dn, mm);
+  HGE_CHECK_LAUNCH(ctx);
+  k_dense_rescale<<<grid_1d(ctx, (int64_t)ne, kBlock), kBlock, 0, ctx->stream>>>(num_edges, R, de, mm);
+  HGE_CHECK_LAUNCH(ctx);
+  hge_dev_free(ctx, mm);
+  if (mem == HGE_MEM_HOST) {
+    HGE_CUDA(cudaMemcpyAsync(xn, dn, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HGE_CUDA(cudaMemcpyAsync(xe, de, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
     HGE_CUDA(cudaEventRecord(ctx->stage_idle, ctx->stream));
     HGE_CUDA(cudaStreamSynchronize(ctx->stream));
   }

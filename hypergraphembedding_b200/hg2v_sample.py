@@ -441,6 +441,33 @@ def SameTypeJaccardSample(indices, idx2features=None, is_edge=None):
                           node_node_prob=_alpha_scale(prob))
 
 
+def DiffTypeJaccardSample(indices, node2edge=None, edge2node=None, num_neighbors=None,
+                          node2features=None, edge2features=None, node2edge_centroid=None,
+                          edge2node_centroid=None):
+  """hg2v_sample.py:343-392 with explicit arguments: neighbour arrays from the global RNG (edges
+  of the node first), the two Jaccard factors as left / right weight, their product as the
+  probability.  The centroid matrices are accepted for compatibility and not needed: the
+  kernel evaluates the centroids on the fly."""
+  del node2edge_centroid, edge2node_centroid
+  assert None not in (node2edge, edge2node, num_neighbors, node2features, edge2features)
+  node_idx, edge_idx = indices
+  assert node2edge.shape[0] == node2features.shape[0]
+  assert node2edge.shape[1] == edge2node.shape[0]
+  assert edge2node.shape[0] == edge2features.shape[0]
+  neighbor_edge_indices = _sample_neighbors(node_idx, node2edge, num_neighbors)
+  neighbor_node_indices = _sample_neighbors(edge_idx, edge2node, num_neighbors)
+  ctx = _native.default_context()
+  nf, ef = _native.FeatureCsr(node2features), _native.FeatureCsr(edge2features)
+  prob_by_node = _native.jaccard_centroid(ctx, nf, _native.CsrArrays(edge2node), nf, [node_idx],
+                                          [edge_idx])[0]
+  prob_by_edge = _native.jaccard_centroid(ctx, ef, _native.CsrArrays(node2edge), ef, [edge_idx],
+                                          [node_idx])[0]
+  return SimilarityRecord(left_node_idx=node_idx, right_edge_idx=edge_idx, left_weight=prob_by_node,
+                          right_weight=prob_by_edge, neighbor_node_indices=neighbor_node_indices,
+                          neighbor_edge_indices=neighbor_edge_indices,
+                          node_edge_prob=_alpha_scale(prob_by_node * prob_by_edge))
+
+
 def WeightedJaccardSamples(hypergraph, node2features, edge2features, num_neighbors, num_samples,
                            run_in_parallel=True, disable_pbar=False):
   """hg2v_sample.py:398-510: node-node / edge-edge samples weighted by the sparse weighted
@@ -621,6 +648,29 @@ def SameTypeDistanceSample(indices, idx2target=None, source_half_emb=None, targe
                             edge_edge_prob=_alpha_scale(prob))
   return SimilarityRecord(left_node_idx=indices[0], right_node_idx=indices[1],
                           node_node_prob=_alpha_scale(prob))
+
+
+def DiffTypeDistanceSample(indices, node2edge=None, edge2node=None, num_neighbors=None,
+                           algebraic_embedding=None):
+  """hg2v_sample.py:588-629 with explicit arguments: neighbour arrays from the global RNG and
+  the max over the node's edges of the edge-edge probability."""
+  assert None not in (node2edge, edge2node, num_neighbors, algebraic_embedding)
+  node_idx, edge_idx = indices
+  neighbor_edge_indices = _sample_neighbors(node_idx, node2edge, num_neighbors)
+  neighbor_node_indices = _sample_neighbors(edge_idx, edge2node, num_neighbors)
+  a, b = _native.CsrArrays(node2edge), _native.CsrArrays(edge2node)
+  xn, xe = embedding_to_arrays(algebraic_embedding, a.shape[0], b.shape[0])
+  ctx = _native.default_context()
+  inc = _native.Incidence(ctx, a.shape[0], b.shape[0], a.ptr, a.idx, b.ptr, b.idx)
+  try:
+    w_e2n = _native.incidence_l2(ctx, inc, xn, xe, order=1, as_weight=True)
+    prob = _native.diff_type_prob(ctx, inc, w_e2n, [node_idx], [edge_idx])[0]
+  finally:
+    inc.close()
+  return SimilarityRecord(left_node_idx=node_idx, right_edge_idx=edge_idx,
+                          neighbor_node_indices=neighbor_node_indices,
+                          neighbor_edge_indices=neighbor_edge_indices,
+                          node_edge_prob=_alpha_scale(prob))
 
 
 ################################################################################

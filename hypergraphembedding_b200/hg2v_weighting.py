@@ -148,6 +148,31 @@ def UniformWeight(hypergraph):
 ################################################################################
 
 
+def _compute_span(idx, idx2neighbors=None, idx_emb=None, neigh_emb=None):
+  """hg2v_weighting.py:214-233 for one row with explicit arguments (ComputeSpans does all rows
+  in one launch): (idx, max(0, max diff) - min(0, min diff)) over the row's neighbours."""
+  assert idx2neighbors is not None and idx_emb is not None and neigh_emb is not None
+  m = csr_matrix(idx2neighbors)
+  if idx not in idx_emb or idx >= m.shape[0]:
+    return idx, 0
+  cols = [int(c) for c in m[idx].indices if int(c) in neigh_emb]
+  if not cols:
+    return idx, 0
+  dim = len(idx_emb[idx].values)
+  x_self = np.asarray([idx_emb[idx].values], dtype=np.float32)
+  x_other = np.asarray([neigh_emb[c].values for c in cols], dtype=np.float32).reshape(len(cols), dim)
+  ctx = _native.default_context()
+  ptr = np.asarray([0, len(cols)], np.int64)
+  ids = np.arange(len(cols), dtype=np.int32)
+  t_ptr = np.arange(len(cols) + 1, dtype=np.int64)
+  inc = _native.Incidence(ctx, 1, len(cols), ptr, ids, t_ptr, np.zeros(len(cols), np.int32))
+  try:
+    span = _native.row_span(ctx, inc, x_self, x_other, 0)[0]
+  finally:
+    inc.close()
+  return idx, span
+
+
 def ComputeSpans(hypergraph, embedding=None, run_in_parallel=True, disable_pbar=False):
   """hg2v_weighting.py:236-293: for every node / edge the spread of its neighbours around it,
   max(0, max(x_neigh - x_self)) - min(0, min(x_neigh - x_self)) over all neighbours and

@@ -124,6 +124,13 @@ int64_t hge_incidence_nnz(const hge_incidence* inc);
 int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R,
                     int iterations, int mem, float* lohi);
 
+/* _helper_scale_embeddings (algebraic_distance.py:97-123) on its own: joint per-column min / max
+ * of the two dense blocks, x <- (x - min) / (max - min), in place.  (hge_algdist_run fuses this
+ * into the half-sweeps; the stand-alone form exists for callers that drive the sweeps
+ * themselves.) */
+int hge_column_rescale(hge_ctx* ctx, float* xn, int64_t num_nodes, float* xe, int64_t num_edges,
+                       int R, int mem);
+
 /* Stepwise form of the same loop, used when the node rows are sharded over several GPUs
  * and the host interleaves collectives (DESIGN.md "Multi-GPU").  All pointers are device
  * pointers. */
