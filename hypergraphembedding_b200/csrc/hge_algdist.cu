@@ -517,6 +517,14 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
   const bool active = own.active, raw_out = own.raw_out;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + own.warp;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
+  // gathered row c of this lane's column = ygl + c * row_bytes: one 32 x 32 + 64 bit multiply-add
+  // per gather instead of a 64-bit index, a scale and a base-pointer reload (155 -> 105
+  // instructions per round of 8 gathers; profiles/r1_half_sweep_experiments.md)
+  const char* const ygl = reinterpret_cast<const char*>(a.yg + c4);
+  const uint32_t row_bytes = (uint32_t)ld4 * (uint32_t)sizeof(float4);
+  auto gather = [&](int c) -> float4 {
+    return __ldg(reinterpret_cast<const float4*>(ygl + (size_t)(uint32_t)c * row_bytes));
+  };
 
   // ---- long rows: one warp per chunk of the row --------------------------------------
   // Loads are software-pipelined: the descriptor of the next chunk and the next block of 32
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
 #pragma unroll
           for (int u = 0; u < UR; ++u) {
             const int c = __shfl_sync(kFull, my, (r0 + u) * G + g);
-            v[u] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+            v[u] = (c >= 0 && active) ? gather(c) : hge_f4_zero();
           }
           accumulate<UR>(acc, comp, v);
         }
@@ -613,7 +621,7 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
-          v[t] = (c >= 0 && active) ? __ldg(a.yg + (size_t)c * ld4 + c4) : hge_f4_zero();
+          v[t] = (c >= 0 && active) ? gather(c) : hge_f4_zero();
         }
         accumulate<8>(acc, comp, v);
 #pragma unroll
