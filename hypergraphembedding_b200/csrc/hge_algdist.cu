@@ -336,8 +336,16 @@ __device__ __forceinline__ void accumulate(float4& s, float4& c, float4 (&v)[N])
 #endif
 }
 
+// Resident blocks per SM and where the per-thread state of a row owner lives.  Measured on config 2
+// (profiles/r1_half_sweep_experiments.md): the kernel waits on memory ~65 % of every warp's time,
+// so what counts is warps per SM.  With the affine-map constants and the running min / max in
+// shared memory (16 registers) the kernel fits 64 registers with 44 bytes of spills: 4 blocks
+// = 32 warps per SM instead of 24, 0.454 -> 0.369 ms per sweep.
+#ifndef HGE_SMEM_STATE
+#define HGE_SMEM_STATE 1
+#endif
 #ifndef HGE_MIN_BLOCKS
-#define HGE_MIN_BLOCKS 3
+#define HGE_MIN_BLOCKS 4
 #endif
 
 // Per-thread state shared by the two gather kernels: which float4 column of which sub-warp this
@@ -349,10 +357,31 @@ struct RowOwner {
   const HalfSweepArgs& a;
   int lane, gl, g, warp, slab, c4, ld4;
   bool active, gaff, raw_out, m0, m1, m2, m3;
+#if HGE_SMEM_STATE
+  // the per-thread constants of the affine map and the running min / max live in shared memory
+  // (read / updated once per finished row): 16 registers less, a fourth resident block per SM
+  float4* sst;   // [4][threads]: inv, invlo, vmin, vmax of this thread
+  int sstride;
+#define HGE_AF_INV sst[0]
+#define HGE_AF_INVLO sst[sstride]
+#define HGE_VMIN sst[2 * sstride]
+#define HGE_VMAX sst[3 * sstride]
+#else
   Affine af;
   float4 vmin, vmax;
+#define HGE_AF_INV af.inv
+#define HGE_AF_INVLO af.invlo
+#define HGE_VMIN vmin
+#define HGE_VMAX vmax
+#endif
 
-  __device__ __forceinline__ explicit RowOwner(const HalfSweepArgs& args) : a(args) {
+  __device__ __forceinline__ explicit RowOwner(const HalfSweepArgs& args, float4* smem_state = nullptr,
+                                               int smem_stride = 0)
+      : a(args) {
+#if HGE_SMEM_STATE
+    sst = smem_state + threadIdx.x;
+    sstride = smem_stride;
+#endif
     lane = threadIdx.x & 31;
     gl = lane & (LPR - 1);
     g = lane / LPR;
@@ -366,8 +395,8 @@ struct RowOwner {
     m1 = col0 + 1 < a.R;
     m2 = col0 + 2 < a.R;
     m3 = col0 + 3 < a.R;
-    af.inv = make_float4(1.f, 1.f, 1.f, 1.f);
-    af.invlo = hge_f4_zero();
+    HGE_AF_INV = make_float4(1.f, 1.f, 1.f, 1.f);
+    HGE_AF_INVLO = hge_f4_zero();
     if (a.mm_prev && active) {
       float lo[4], inv[4];
 #pragma unroll
@@ -380,14 +409,14 @@ struct RowOwner {
           inv[j] = 1.0f / (hi - lo[j]);
         }
       }
-      af.inv = make_float4(inv[0], inv[1], inv[2], inv[3]);
-      af.invlo = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
+      HGE_AF_INV = make_float4(inv[0], inv[1], inv[2], inv[3]);
+      HGE_AF_INVLO = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
     }
     gaff = a.gather_affine != 0;
     raw_out = a.raw_out != 0;
     const float inf = __int_as_float(0x7f800000);
-    vmin = make_float4(inf, inf, inf, inf);
-    vmax = make_float4(-inf, -inf, -inf, -inf);
+    HGE_VMIN = make_float4(inf, inf, inf, inf);
+    HGE_VMAX = make_float4(-inf, -inf, -inf, -inf);
   }
 
   // called by the lanes that own (row, c4); acc is the full gathered sum
@@ -413,13 +442,19 @@ struct RowOwner {
       }
       return;
     }
-    const float4 x = finalize_value(yown, acc, degf, invs, af, gaff);
+    Affine afv;
+    afv.inv = HGE_AF_INV;
+    afv.invlo = HGE_AF_INVLO;
+    const float4 x = finalize_value(yown, acc, degf, invs, afv, gaff);
     const float w = __frcp_rn(degf);
     a.yo[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
-    if (m0) { vmin.x = fminf(vmin.x, x.x); vmax.x = fmaxf(vmax.x, x.x); }
-    if (m1) { vmin.y = fminf(vmin.y, x.y); vmax.y = fmaxf(vmax.y, x.y); }
-    if (m2) { vmin.z = fminf(vmin.z, x.z); vmax.z = fmaxf(vmax.z, x.z); }
-    if (m3) { vmin.w = fminf(vmin.w, x.w); vmax.w = fmaxf(vmax.w, x.w); }
+    float4 lo4 = HGE_VMIN, hi4 = HGE_VMAX;
+    if (m0) { lo4.x = fminf(lo4.x, x.x); hi4.x = fmaxf(hi4.x, x.x); }
+    if (m1) { lo4.y = fminf(lo4.y, x.y); hi4.y = fmaxf(hi4.y, x.y); }
+    if (m2) { lo4.z = fminf(lo4.z, x.z); hi4.z = fmaxf(hi4.z, x.z); }
+    if (m3) { lo4.w = fminf(lo4.w, x.w); hi4.w = fmaxf(hi4.w, x.w); }
+    HGE_VMIN = lo4;
+    HGE_VMAX = hi4;
   }
 
   __device__ __forceinline__ float4 load_own(int row) const {
@@ -470,20 +505,21 @@ struct RowOwner {
   template <int WARPS>
   __device__ __forceinline__ void publish_minmax(float4 (*smin)[LPR], float4 (*smax)[LPR]) {
     if (raw_out) return;    // uniform over the grid
+    float4 lo4 = HGE_VMIN, hi4 = HGE_VMAX;
 #pragma unroll
     for (int off = LPR; off < 32; off <<= 1) {
-      vmin.x = fminf(vmin.x, __shfl_xor_sync(kFull, vmin.x, off));
-      vmin.y = fminf(vmin.y, __shfl_xor_sync(kFull, vmin.y, off));
-      vmin.z = fminf(vmin.z, __shfl_xor_sync(kFull, vmin.z, off));
-      vmin.w = fminf(vmin.w, __shfl_xor_sync(kFull, vmin.w, off));
-      vmax.x = fmaxf(vmax.x, __shfl_xor_sync(kFull, vmax.x, off));
-      vmax.y = fmaxf(vmax.y, __shfl_xor_sync(kFull, vmax.y, off));
-      vmax.z = fmaxf(vmax.z, __shfl_xor_sync(kFull, vmax.z, off));
-      vmax.w = fmaxf(vmax.w, __shfl_xor_sync(kFull, vmax.w, off));
+      lo4.x = fminf(lo4.x, __shfl_xor_sync(kFull, lo4.x, off));
+      lo4.y = fminf(lo4.y, __shfl_xor_sync(kFull, lo4.y, off));
+      lo4.z = fminf(lo4.z, __shfl_xor_sync(kFull, lo4.z, off));
+      lo4.w = fminf(lo4.w, __shfl_xor_sync(kFull, lo4.w, off));
+      hi4.x = fmaxf(hi4.x, __shfl_xor_sync(kFull, hi4.x, off));
+      hi4.y = fmaxf(hi4.y, __shfl_xor_sync(kFull, hi4.y, off));
+      hi4.z = fmaxf(hi4.z, __shfl_xor_sync(kFull, hi4.z, off));
+      hi4.w = fmaxf(hi4.w, __shfl_xor_sync(kFull, hi4.w, off));
     }
     if (g == 0) {
-      smin[warp][gl] = vmin;
-      smax[warp][gl] = vmax;
+      smin[warp][gl] = lo4;
+      smax[warp][gl] = hi4;
     }
     __syncthreads();
     if (threadIdx.x < LPR * 4) {
@@ -512,7 +548,12 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
   constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
   constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
 
+#if HGE_SMEM_STATE
+  __shared__ float4 s_state[4 * kBlock];
+  RowOwner<LPR> own(a, s_state, kBlock);
+#else
   RowOwner<LPR> own(a);
+#endif
   const int lane = own.lane, gl = own.gl, g = own.g, c4 = own.c4, ld4 = own.ld4;
   const bool active = own.active, raw_out = own.raw_out;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + own.warp;
@@ -695,7 +736,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_heavy_bulk(const HalfSweepArg
   constexpr int G = 32 / LPR;
   constexpr int ROW4 = LPR;                          // float4 slots per staged row
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#if HGE_SMEM_STATE
+  __shared__ float4 s_state_bulk[4 * WARPS * 32];
+  RowOwner<LPR> own(a, s_state_bulk, WARPS * 32);
+#else
   RowOwner<LPR> own(a);
+#endif
   const int lane = own.lane, gl = own.gl, g = own.g, ld4 = own.ld4;
   const bool active = own.active, raw_out = own.raw_out;
   float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)own.warp * STAGES * 32 * ROW4;
