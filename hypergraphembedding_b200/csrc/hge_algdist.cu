@@ -1587,19 +1587,3 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
 }
 
 }  // extern "C"
-
-// Host copy of the row pointers of one CSR (the weighting entry points cut rows into segments
-// on the host); fetched from the device on first use.
-int hge_incidence_host_ptr(hge_incidence* inc, int order, const std::vector<int64_t>** out) {
-  std::vector<int64_t>& h = order == 0 ? inc->h_n2e_ptr : inc->h_e2n_ptr;
-  const size_t n = (size_t)(order == 0 ? inc->N : inc->E) + 1;
-  if (h.size() != n) {
-    h.resize(n);
-    hge_ctx* ctx = inc->ctx;
-    HGE_CUDA(cudaMemcpyAsync(h.data(), order == 0 ? inc->n2e_ptr : inc->e2n_ptr, n * 8,
-                             cudaMemcpyDeviceToHost, ctx->stream));
-    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  *out = &h;
-  return HGE_OK;
-}

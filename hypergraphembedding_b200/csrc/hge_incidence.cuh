@@ -79,7 +79,6 @@ struct hge_incidence {
   int32_t* n2e_idx = nullptr;
   int64_t* e2n_ptr = nullptr;
   int32_t* e2n_idx = nullptr;
-  std::vector<int64_t> h_n2e_ptr, h_e2n_ptr;
   HgeHalfSchedule node_half, edge_half;
   // shard of a row-partitioned hypergraph (hge_incidence_create_sharded): local node rows, all
   // edges; the edge half is additionally cut into slices of consecutive edges
@@ -97,8 +96,6 @@ struct hge_incidence {
   int64_t* tile_pos = nullptr;     // device [(tiles + 1) x E] incidence offsets
   int32_t tile_rows = 0;
 };
-
-int hge_incidence_host_ptr(hge_incidence* inc, int order, const std::vector<int64_t>** out);
 
 // Peer-memory exchange arena of one shard (csrc/hge_p2p.cu): one cudaMalloc block, exported to
 // the other ranks of the node through CUDA IPC.

@@ -5,6 +5,7 @@
 // are read as float4 by sub-warps of LPR lanes (LPR = next power of two of ceil(R / 4), at
 // most 32), several pairs in flight per lane; dense inputs whose rows are not 16-byte aligned
 // (R % 4 != 0) are first copied into a zero-padded buffer.
+#include <cub/device/device_scan.cuh>
 #include <math.h>
 
 #include <algorithm>
@@ -356,30 +357,64 @@ __global__ void __launch_bounds__(kBlock) k_diff_type_prob(
   }
 }
 
-// rows -> segments of at most kSegment incidences (host side; row pointers are on the host)
+// rows -> segments of at most kSegment incidences, on the device: per row ceil(deg / kSegment)
+// segments, an exclusive prefix sum for their positions (cub; set-up), one thread per row writes
+// them.  (A host loop over the row pointers did this before: two passes over 1.5 M rows, a 24 MB
+// upload and a stream drain per call on the 1M-node workload.)
 constexpr int kSegment = 2048;
 
-int build_segments(const hge_ctx* ctx, const std::vector<int64_t>& ptr, Segment** d_segs,
-                   int64_t* count) {
-  std::vector<Segment> segs;
-  segs.reserve(ptr.size());
-  const int32_t rows = (int32_t)ptr.size() - 1;
-  for (int32_t r = 0; r < rows; ++r) {
+__global__ void k_segment_counts(int32_t rows, const int64_t* __restrict__ ptr,
+                                 int64_t* __restrict__ counts) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    counts[r] = (ptr[r + 1] - ptr[r] + kSegment - 1) / kSegment;
+}
+
+__global__ void k_segment_write(int32_t rows, const int64_t* __restrict__ ptr,
+                                const int64_t* __restrict__ offset, Segment* __restrict__ segs) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t at = offset[r];
     for (int64_t s = ptr[r]; s < ptr[r + 1]; s += kSegment) {
       Segment sg;
-      sg.row = r;
+      sg.row = (int32_t)r;
       sg.start = s;
-      sg.count = (int32_t)std::min<int64_t>(kSegment, ptr[r + 1] - s);
-      segs.push_back(sg);
+      sg.count = (int32_t)min((int64_t)kSegment, ptr[r + 1] - s);
+      segs[at++] = sg;
     }
   }
-  *count = (int64_t)segs.size();
-  HGE_TRY(hge_dev_alloc(ctx, d_segs, segs.size()));
-  if (!segs.empty()) {
-    HGE_CUDA(cudaMemcpyAsync(*d_segs, segs.data(), segs.size() * sizeof(Segment),
-                             cudaMemcpyHostToDevice, ctx->stream));
-    HGE_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
+}
+
+int build_segments(hge_ctx* ctx, int32_t rows, const int64_t* d_ptr, int64_t nnz, Segment** d_segs,
+                   int64_t* count) {
+  *d_segs = nullptr;
+  *count = 0;
+  if (rows <= 0) return HGE_OK;
+  int64_t *counts = nullptr, *offset = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &counts, (size_t)rows + 1));
+  HGE_TRY(hge_dev_alloc(ctx, &offset, (size_t)rows + 1));
+  HGE_CUDA(cudaMemsetAsync(counts + rows, 0, sizeof(int64_t), ctx->stream));
+  const int grid = grid_for(ctx, rows, kBlock);
+  k_segment_counts<<<grid, kBlock, 0, ctx->stream>>>(rows, d_ptr, counts);
+  HGE_CHECK_LAUNCH(ctx);
+  size_t temp_bytes = 0;
+  HGE_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, offset, rows + 1, ctx->stream));
+  char* temp = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &temp, temp_bytes));
+  HGE_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offset, rows + 1, ctx->stream));
+  ctx->launches += 1;
+  // the segment count is bounded without a read-back: every row adds at most one partial segment
+  const int64_t bound = nnz / kSegment + rows;
+  HGE_TRY(hge_dev_alloc(ctx, d_segs, (size_t)bound));
+  k_segment_write<<<grid, kBlock, 0, ctx->stream>>>(rows, d_ptr, offset, *d_segs);
+  HGE_CHECK_LAUNCH(ctx);
+  int64_t total = 0;
+  HGE_CUDA(cudaMemcpyAsync(&total, offset + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  hge_dev_free(ctx, temp);
+  hge_dev_free(ctx, counts);
+  hge_dev_free(ctx, offset);
+  *count = total;
   return HGE_OK;
 }
 
@@ -404,9 +439,6 @@ int hge_incidence_l2(hge_ctx* ctx, hge_incidence* inc, const float* xn, const fl
   HGE_REQUIRE(order == 0 || order == 1, "hge_incidence_l2: order must be 0 or 1");
   HGE_CUDA(cudaSetDevice(ctx->device));
   const HgeHalfSchedule& half = order == 0 ? inc->node_half : inc->edge_half;
-  const std::vector<int64_t>* h_ptr_p = nullptr;
-  HGE_TRY(hge_incidence_host_ptr(inc, order, &h_ptr_p));
-  const std::vector<int64_t>& h_ptr = *h_ptr_p;
   Staged<float> s_xn, s_xe, s_out;
   HGE_TRY(s_xn.init(ctx, xn, (size_t)inc->N * R, mem, true, false));
   HGE_TRY(s_xe.init(ctx, xe, (size_t)inc->E * R, mem, true, false));
@@ -416,7 +448,7 @@ int hge_incidence_l2(hge_ctx* ctx, hge_incidence* inc, const float* xn, const fl
   HGE_TRY(pe.init(ctx, s_xe.dev, inc->E, R));
   Segment* segs = nullptr;
   int64_t nseg = 0;
-  HGE_TRY(build_segments(ctx, h_ptr, &segs, &nseg));
+  HGE_TRY(build_segments(ctx, half.rows, half.ptr, half.nnz, &segs, &nseg));
   const int ld4 = ((R + 3) & ~3) / 4;
   const float max_dist = (float)sqrt((double)R);
   const float4* self = order == 0 ? pn.rows4 : pe.rows4;
