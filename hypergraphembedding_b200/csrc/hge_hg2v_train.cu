@@ -182,16 +182,40 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       load_row<DPL>(a.E, re, dim, lane, Re);
       const float z_nn = dot<DPL>(Ln, Rn), z_ee = dot<DPL>(Le, Re);
       const float p_nn = activate(z_nn, a.activation), p_ee = activate(z_ee, a.activation);
-      // neighbourhood terms: lane i keeps the pre-activation of neighbour i of either kind
+      // neighbourhood terms: lane i keeps the pre-activation of neighbour i of either kind.
+      // With dim <= 32 and k <= 8 all 2k neighbour rows are loaded up front (one memory latency
+      // instead of 2k dependent ones) and stay in registers for the gradient pass.
+      constexpr int KM = 8;
+      const bool preload = DPL == 1 && k <= KM;
+      float nbN[KM], nbE[KM];
       float za_mine = 0.0f, zb_mine = 0.0f;
-      for (int i = 0; i < k; ++i) {
-        load_row<DPL>(a.N, __shfl_sync(kFull, my, 4 + i), dim, lane, X);
-        const float za = dot<DPL>(X, Ln);
-        load_row<DPL>(a.E, __shfl_sync(kFull, my, 4 + k + i), dim, lane, X);
-        const float zb = dot<DPL>(X, Re);
-        if (lane == i) {
-          za_mine = za;
-          zb_mine = zb;
+      if (preload) {
+#pragma unroll
+        for (int i = 0; i < KM; ++i) {
+          const int32_t xn = __shfl_sync(kFull, my, (4 + i) & 31), xe = __shfl_sync(kFull, my, (4 + k + i) & 31);
+          nbN[i] = (i < k && lane < dim) ? __ldcg(a.N + (size_t)xn * dim + lane) : 0.0f;
+          nbE[i] = (i < k && lane < dim) ? __ldcg(a.E + (size_t)xe * dim + lane) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < KM; ++i) {
+          if (i < k) {
+            const float za = warp_sum(nbN[i] * Ln[0]), zb = warp_sum(nbE[i] * Re[0]);
+            if (lane == i) {
+              za_mine = za;
+              zb_mine = zb;
+            }
+          }
+        }
+      } else {
+        for (int i = 0; i < k; ++i) {
+          load_row<DPL>(a.N, __shfl_sync(kFull, my, 4 + i), dim, lane, X);
+          const float za = dot<DPL>(X, Ln);
+          load_row<DPL>(a.E, __shfl_sync(kFull, my, 4 + k + i), dim, lane, X);
+          const float zb = dot<DPL>(X, Re);
+          if (lane == i) {
+            za_mine = za;
+            zb_mine = zb;
+          }
         }
       }
       const float a_mine = lane < k ? activate(za_mine, a.activation) : 0.0f;
@@ -215,20 +239,38 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         gLn[j] = d_nn * Rn[j];
         gRe[j] = d_ee * Le[j];
       }
-      for (int i = 0; i < k; ++i) {
-        const float da = __shfl_sync(kFull, da_mine, i), db = __shfl_sync(kFull, db_mine, i);
-        const int32_t xn = __shfl_sync(kFull, my, 4 + i), xe = __shfl_sync(kFull, my, 4 + k + i);
-        if (da != 0.0f) {
-          load_row<DPL>(a.N, xn, dim, lane, X);
+      if (preload) {
 #pragma unroll
-          for (int j = 0; j < DPL; ++j) gLn[j] = fmaf(da, X[j], gLn[j]);
-          add_grad<DPL>(a.gN, s_g0[0], xn, dim, lane, da, Ln);
+        for (int i = 0; i < KM; ++i) {
+          if (i < k) {
+            const float da = __shfl_sync(kFull, da_mine, i), db = __shfl_sync(kFull, db_mine, i);
+            const int32_t xn = __shfl_sync(kFull, my, 4 + i), xe = __shfl_sync(kFull, my, 4 + k + i);
+            if (da != 0.0f) {
+              gLn[0] = fmaf(da, nbN[i], gLn[0]);
+              add_grad<DPL>(a.gN, s_g0[0], xn, dim, lane, da, Ln);
+            }
+            if (db != 0.0f) {
+              gRe[0] = fmaf(db, nbE[i], gRe[0]);
+              add_grad<DPL>(a.gE, s_g0[1], xe, dim, lane, db, Re);
+            }
+          }
         }
-        if (db != 0.0f) {
-          load_row<DPL>(a.E, xe, dim, lane, X);
+      } else {
+        for (int i = 0; i < k; ++i) {
+          const float da = __shfl_sync(kFull, da_mine, i), db = __shfl_sync(kFull, db_mine, i);
+          const int32_t xn = __shfl_sync(kFull, my, 4 + i), xe = __shfl_sync(kFull, my, 4 + k + i);
+          if (da != 0.0f) {
+            load_row<DPL>(a.N, xn, dim, lane, X);
 #pragma unroll
-          for (int j = 0; j < DPL; ++j) gRe[j] = fmaf(db, X[j], gRe[j]);
-          add_grad<DPL>(a.gE, s_g0[1], xe, dim, lane, db, Re);
+            for (int j = 0; j < DPL; ++j) gLn[j] = fmaf(da, X[j], gLn[j]);
+            add_grad<DPL>(a.gN, s_g0[0], xn, dim, lane, da, Ln);
+          }
+          if (db != 0.0f) {
+            load_row<DPL>(a.E, xe, dim, lane, X);
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) gRe[j] = fmaf(db, X[j], gRe[j]);
+            add_grad<DPL>(a.gE, s_g0[1], xe, dim, lane, db, Re);
+          }
         }
       }
       add_grad<DPL>(a.gN, s_g0[0], ln, dim, lane, 1.0f, gLn);
@@ -263,12 +305,44 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const bool node = lane == 0 || lane == 2 || (lane >= 4 && lane < 4 + k);
         old = atomicExch((node ? a.claimN : a.claimE) + my, stamp);
       }
-      for (int c = 0; c < cols; ++c) {
-        if (__shfl_sync(kFull, old, c) == stamp) continue;   // another warp (or column) owns it
-        const int32_t row = __shfl_sync(kFull, my, c);
-        const bool node = c == 0 || c == 2 || (c >= 4 && c < 4 + k);
-        if (node) apply_row(a.N, a.accN, a.gN, row, dim, lane, a.lr, a.eps);
-        else apply_row(a.E, a.accE, a.gE, row, dim, lane, a.lr, a.eps);
+      // the rows this warp owns, four at a time: all loads of a group first, then the updates
+      unsigned owned = __ballot_sync(kFull, lane < cols && old != stamp);
+      while (owned) {
+        int32_t rw[4] = {0, 0, 0, 0};
+        unsigned is_node = 0;
+        int nr = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (owned) {
+            const int c = __ffs(owned) - 1;
+            owned &= owned - 1;
+            rw[j] = __shfl_sync(kFull, my, c);
+            if (c == 0 || c == 2 || (c >= 4 && c < 4 + k)) is_node |= 1u << j;
+            nr = j + 1;
+          }
+        }
+        for (int c = lane; c < dim; c += 32) {
+          float gv[4], av[4], pv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const size_t at = (size_t)rw[j] * dim + c;
+            const bool node = (is_node >> j) & 1;
+            gv[j] = j < nr ? __ldcg((node ? a.gN : a.gE) + at) : 0.0f;
+            av[j] = j < nr ? __ldcg((node ? a.accN : a.accE) + at) : 0.0f;
+            pv[j] = j < nr ? __ldcg((node ? a.N : a.E) + at) : 0.0f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nr && gv[j] != 0.0f) {
+              const size_t at = (size_t)rw[j] * dim + c;
+              const bool node = (is_node >> j) & 1;
+              const float acc = av[j] + gv[j] * gv[j];
+              (node ? a.accN : a.accE)[at] = acc;
+              (node ? a.N : a.E)[at] = pv[j] - a.lr * gv[j] / (sqrtf(acc) + a.eps);
+              (node ? a.gN : a.gE)[at] = 0.0f;
+            }
+          }
+        }
       }
     }
     cluster.sync();
