@@ -203,6 +203,21 @@ def cpu_baseline_port(A, B, spec, sweeps, threads=0):
   return A.nnz * spec["R"] * sweeps / dt, dt, (threads or cport.max_threads())
 
 
+def cpu_baseline_scipy(A, B, spec, sweeps=2):
+  """the vectorised scipy f64 restatement of the same arithmetic
+  (oracle/port.py, validated against the reference to 3e-8) on one core -- scipy's sparse
+  products are single-threaded -- on a bounded sample of the workload's sweeps."""
+  from hypergraphembedding_b200 import synthetic
+  from oracle import port
+  xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], spec["R"], seed=0)
+  t = time.time()
+  port.algdist_vectorised(A, B, xn0, xe0, sweeps)
+  dt = time.time() - t
+  return {"value": A.nnz * spec["R"] * sweeps / dt, "unit": "nnz*R*iters/s", "cores": 1, "kind": "port",
+          "sample": "%d of %d sweeps of the full workload, scipy CSR products in f64 (%.1f s)"
+                    % (sweeps, spec["sweeps"], dt)}
+
+
 def run_reference(args, spec):
   """--impl reference: the reference's CPU implementation of the path on this box's host cores.
   The reference is pure Python (there is nothing of it to compile into oracle/_ref) and its
@@ -583,6 +598,10 @@ def run_ours(args, spec):
 
   cpu_sweeps = sweeps
   cpu_value, cpu_dt, cpu_threads = cpu_baseline_port(A, B, spec, cpu_sweeps)
+  try:
+    scipy_line = cpu_baseline_scipy(A, B, spec)
+  except Exception as exc:
+    scipy_line = {"error": "%s: %s" % (type(exc).__name__, exc)}
   extras = {}
   if not args.no_extras:
     for key, fn in (("hobe", hobe_extra), ("hg2v_train", hg2v_train_extra),
@@ -614,7 +633,7 @@ def run_ours(args, spec):
                        "sample": "the full workload, %d of %d sweeps, C restatement of the reference's "
                                  "per-row f64 arithmetic on all host threads (%.1f s)"
                                  % (cpu_sweeps, sweeps, cpu_dt),
-                       "host_cores": os.cpu_count()},
+                       "host_cores": os.cpu_count(), "scipy_restatement_one_core": scipy_line},
       "e2e": {"value": nnz * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
               "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
       "gpu_launches": int(launches),
