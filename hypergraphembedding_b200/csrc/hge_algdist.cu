@@ -952,6 +952,10 @@ int occupancy_grid(const hge_ctx* ctx, int* out) {
   int per_sm = 0;
   HGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_half_sweep<LPR>, kBlock, 0));
   if (per_sm < 1) per_sm = 1;
+  // four waves of blocks rather than one persistent wave: the work list is dealt round-robin, so
+  // blocks of later waves fill the SMs that finish early (long rows make the shares uneven);
+  // measured 0.371 -> 0.353 ms per sweep on config 2
+  per_sm *= 4;
   if (ctx->blocks_per_sm > 0) per_sm = ctx->blocks_per_sm;
   *out = per_sm * ctx->num_sms;
   return HGE_OK;

@@ -88,9 +88,11 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->own_stream = false;
-  ctx->light_max_deg = 64;
-  ctx->chunk = 512;
-  ctx->blocks_per_sm = 0;  // 0: ask the occupancy calculator
+  // schedule defaults from the sweep in profiles/r1_half_sweep_experiments.md (config 2, 4-block
+  // kernel): sub-warp rows up to degree 128, chunks of 1024, a grid of 4 x the resident blocks
+  ctx->light_max_deg = 128;
+  ctx->chunk = 1024;
+  ctx->blocks_per_sm = 0;  // 0: 4 x what the occupancy calculator says is resident
   // measured slower than the register gather (profiles/r1_bulk_copy_experiment.md): opt-in
   ctx->use_bulk = 0;
   if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;

@@ -58,9 +58,9 @@ int hge_ctx_destroy(hge_ctx* ctx);
 int hge_ctx_set_stream(hge_ctx* ctx, void* stream);
 int hge_ctx_sync(hge_ctx* ctx);
 /* Tuning knobs of the relaxation schedule (0 keeps the default):
- *   light_max_deg  rows up to this degree are gathered by one sub-warp (<= 255)
- *   chunk          incidences per warp work item for longer rows
- *   blocks_per_sm  persistent grid size = SMs * blocks_per_sm */
+ *   light_max_deg  rows up to this degree are gathered by one sub-warp (<= 255; default 128)
+ *   chunk          incidences per warp work item for longer rows (default 1024)
+ *   blocks_per_sm  grid size = SMs * blocks_per_sm (default: 4 x the resident blocks) */
 int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_per_sm);
 /* Experimental: gather the long rows (more than light_max_deg incidences) through the
  * bulk-copy engine (cp.async.bulk into a shared-memory ring, k_heavy_bulk) instead of the
