@@ -15,6 +15,10 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_NAME = "libhge_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 
+# host-only sources (.cpp) go through g++ directly: they use x86 intrinsics with per-function
+# target attributes, which nvcc's front end does not take
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread"]
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-Xptxas", "-v",
@@ -55,7 +59,12 @@ def build(force=False, verbose=False, defines=(), out=None, tag=""):
   for src in sources():
     obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
     objs.append(obj)
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c", src, "-o", obj]
+    if src.endswith(".cpp"):
+      cuda_inc = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "include")
+      cmd = [os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-I", cuda_inc] + ["-D" + d for d in defines] + [
+          "-c", src, "-o", obj]
+    else:
+      cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-x", "cu", "-c", src, "-o", obj]
     procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                         text=True)))
   log = []
@@ -72,7 +81,8 @@ def build(force=False, verbose=False, defines=(), out=None, tag=""):
     raise RuntimeError("nvcc failed; see the log above")
   tmp = out + ".tmp"
   subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-gencode",
-                                                               "arch=compute_100a,code=sm_100a"])
+                                                               "arch=compute_100a,code=sm_100a",
+                                                               "-Xlinker", "-lpthread"])
   os.replace(tmp, out)
   return out
 

@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <immintrin.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -122,23 +123,56 @@ struct Mt19937 {
     }
   }
 
-  // The draws of a Fisher-Yates shuffle of n items, j[i] = interval(i) for i = n-1 .. 1, by the
-  // same branch-free filter; the bound (and, at powers of two, the mask) shrinks by one with
-  // every accepted output.
-  void shuffle_draws(uint32_t n, uint32_t* j) {
+  // The draws of a Fisher-Yates shuffle of n items in the order they are consumed: out[q] =
+  // interval(n - 1 - q) for q = 0 .. n - 2, by the same branch-free filter; the bound (and, at
+  // powers of two, the mask) shrinks by one with every accepted output.  Where the bound is far
+  // from the next power of two, 16 words are decided at once (AVX-512): word p of a block is
+  // accepted for sure if it is <= bound - p (at most p outputs were accepted before it) and
+  // rejected for sure if it is > bound; a block with a word in between is left to the scalar
+  // filter.  Same stream, same results -- only faster on long rows.
+  void shuffle_draws(uint32_t n, uint32_t* out) {
     if (n < 2) return;
+    static const bool wide = __builtin_cpu_supports("avx512f");
     uint32_t i = n - 1, mask = mask_of(i);
+    size_t q = 0;
     while (i >= 1) {
       if (pos >= 624) advance_generation();
       int p = pos;
-      while (p < 1248 && i >= 1) {
+      if (wide) {
+        while (p + 16 <= 1248 && i >= (mask >> 1) + 16) {
+          const int c = filter16(tempered + p, mask, i, out + q);
+          if (c < 0) break;
+          p += 16;
+          q += (size_t)c;
+          i -= (uint32_t)c;
+          mask = (i <= (mask >> 1)) ? (mask >> 1) : mask;   // a full block can end on the boundary
+        }
+      }
+      const int limit = p + 16 < 1248 ? p + 16 : 1248;
+      while (p < limit && i >= 1) {
         const uint32_t v = tempered[p++] & mask;
-        j[i] = v;
-        i -= (v <= i);
+        out[q] = v;
+        const uint32_t acc = v <= i;
+        q += acc;
+        i -= acc;
         mask = (i <= (mask >> 1)) ? (mask >> 1) : mask;
       }
       pos = p;
     }
+  }
+
+  // 16 tempered words against bound i with a constant mask: number accepted (their masked values
+  // appended to out), or -1 when a word cannot be decided without the ones before it.
+  __attribute__((target("avx512f"))) static int filter16(const uint32_t* w, uint32_t mask, uint32_t i,
+                                                         uint32_t* out) {
+    const __m512i v = _mm512_and_si512(_mm512_loadu_si512(w), _mm512_set1_epi32((int)mask));
+    const __m512i lane = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    const __m512i top = _mm512_set1_epi32((int)i);
+    const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_sub_epi32(top, lane));
+    const __mmask16 maybe = _mm512_cmple_epu32_mask(v, top);
+    if (sure != maybe) return -1;
+    _mm512_mask_compressstoreu_epi32(out, sure, v);
+    return __builtin_popcount((unsigned)sure);
   }
 };
 
@@ -309,7 +343,7 @@ class SamplePipeline {
         // np.random.choice(cols, min(k, n), replace=False) == cols[permutation(n)[:k]]
         perm.resize((size_t)n);
         for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
-        for (int64_t i = n - 1; i >= 1; --i) std::swap(perm[(size_t)i], perm[d[i]]);
+        for (int64_t i = n - 1, t = 0; i >= 1; --i, ++t) std::swap(perm[(size_t)i], perm[d[t]]);
         for (int32_t q = 0; q < cnt; ++q) {
           out_row_[o + q] = r;
           out_col_[o + q] = cand[(size_t)perm[(size_t)q]];
@@ -580,7 +614,8 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
         draws.resize((size_t)n);
         for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
         g.mt.shuffle_draws((uint32_t)n, draws.data());
-        for (int64_t i = n - 1; i >= 1; --i) std::swap(perm[(size_t)i], perm[draws[(size_t)i]]);
+        for (int64_t i = n - 1, t = 0; i >= 1; --i, ++t)
+          std::swap(perm[(size_t)i], perm[draws[(size_t)t]]);
         for (int64_t s = 0; s < k; ++s)
           if (!emit(r, cand[(size_t)perm[(size_t)s]])) goto full;
       } else {

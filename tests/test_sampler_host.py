@@ -129,3 +129,25 @@ def test_fixture_scale_candidates_match_golden_hash():
                     ((b, a, b), B * B.T * B)):
     ptr_, idx_ = _native.spgemm_rows(mats, np.arange(ref.shape[0]))
     assert np.array_equal(ptr_, ref.indptr) and np.array_equal(idx_, ref.indices)
+
+
+@pytest.mark.parametrize("n", [2, 15, 16, 17, 31, 32, 33, 47, 48, 100, 255, 256, 257, 271, 272, 273, 1000,
+                               4095, 4096, 4097, 4112, 70000])
+def test_shuffle_of_every_length_class_equals_numpy_choice(n):
+  """np.random.choice(cols, k, replace=False) on a row of n candidates: the block filter of the
+  draw loop (16 words at a time where the bound is far from a power of two, scalar near the
+  boundaries) must consume the stream exactly as numpy's rk_interval does -- same samples, same
+  final state -- for lengths on both sides of every switch-over."""
+  import scipy.sparse as sps
+  from hypergraphembedding_b200.hg2v_sample import _sample_adj_matrix
+  cols = np.arange(0, 3 * n, 3)
+  m = sps.csr_matrix((np.ones(n, dtype=bool), cols, [0, n]), shape=(1, 3 * n))
+  for seed, k in ((1, 1), (2, min(n, 7)), (3, n)):
+    np.random.seed(seed)
+    want = np.random.choice(cols, k, replace=False)
+    want_state = np.random.get_state()
+    np.random.seed(seed)
+    got = _sample_adj_matrix(m, [0], k)
+    state = np.random.get_state()
+    assert [c for _, c in got] == want.tolist()
+    assert state[2] == want_state[2] and np.array_equal(state[1], want_state[1])
