@@ -110,10 +110,18 @@ struct Mt19937 {
       return;
     }
     const uint32_t mask = mask_of(mx);
+    static const bool wide = __builtin_cpu_supports("avx512f");
     int64_t c = 0;
     while (c < count) {
       if (pos >= 624) advance_generation();
       int p = pos;
+      if (wide) {
+        // constant bound: 16 words at a time while a whole block still fits into `count`
+        while (p + 16 <= 1248 && count - c >= 16) {
+          c += accept16(tempered + p, mask, mx, out + c);
+          p += 16;
+        }
+      }
       while (p < 1248 && c < count) {
         const uint32_t v = tempered[p++] & mask;
         out[c] = v;
@@ -121,6 +129,16 @@ struct Mt19937 {
       }
       pos = p;
     }
+  }
+
+  __attribute__((target("avx512f"))) static int accept16(const uint32_t* w, uint32_t mask, uint32_t mx,
+                                                         uint32_t* out) {
+    const __m512i v = _mm512_and_si512(_mm512_loadu_si512(w), _mm512_set1_epi32((int)mask));
+    const __mmask16 ok = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)mx));
+    // register compress + full 64-byte store (the masked compress-store to memory is slow);
+    // callers leave 16 words of slack behind the region being filled
+    _mm512_storeu_si512(out, _mm512_maskz_compress_epi32(ok, v));
+    return __builtin_popcount((unsigned)ok);
   }
 
   // The draws of a Fisher-Yates shuffle of n items in the order they are consumed: out[q] =
@@ -171,7 +189,7 @@ struct Mt19937 {
     const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_sub_epi32(top, lane));
     const __mmask16 maybe = _mm512_cmple_epu32_mask(v, top);
     if (sure != maybe) return -1;
-    _mm512_mask_compressstoreu_epi32(out, sure, v);
+    _mm512_storeu_si512(out, _mm512_maskz_compress_epi32(sure, v));
     return __builtin_popcount((unsigned)sure);
   }
 };
@@ -549,7 +567,7 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
         blk->doff[(size_t)k] = need;
         if (n > 0) need += replace ? samples_per_row[r0 + k] : n;
       }
-      blk->draws.resize((size_t)std::max<int64_t>(need, 1));
+      blk->draws.resize((size_t)need + 16);   // 16 words of slack for the block filter's stores
       for (int64_t k = 0; k < nrows; ++k) {
         const int64_t n = blk->ptr[(size_t)k + 1] - blk->ptr[(size_t)k];
         if (n == 0) continue;   // hg2v_sample.py:79
@@ -611,7 +629,7 @@ int hge_sample_adj_rows(int kind, const int64_t* p1, const int32_t* i1, const in
         // np.random.choice(cols, min(k, n), replace=False) == cols[permutation(n)[:k]]
         const int64_t k = std::min<int64_t>(want, n);
         perm.resize((size_t)n);
-        draws.resize((size_t)n);
+        draws.resize((size_t)n + 16);
         for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
         g.mt.shuffle_draws((uint32_t)n, draws.data());
         for (int64_t i = n - 1, t = 0; i >= 1; --i, ++t)
