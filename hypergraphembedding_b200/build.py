@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 
 # host-only sources (.cpp) go through g++ directly: they use x86 intrinsics with per-function
 # target attributes, which nvcc's front end does not take
-CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-psabi", "-pthread"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

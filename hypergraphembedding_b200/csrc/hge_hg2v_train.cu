@@ -120,22 +120,6 @@ __device__ __forceinline__ float dot(const float (&a)[DPL], const float (&b)[DPL
   return warp_sum(s);
 }
 
-// Adagrad on one claimed row; clears the row's gradient.
-__device__ __forceinline__ void apply_row(float* __restrict__ p, float* __restrict__ acc,
-                                          float* __restrict__ g, int32_t row, int dim, int lane,
-                                          float lr, float eps) {
-  for (int c = lane; c < dim; c += 32) {
-    const size_t at = (size_t)row * dim + c;
-    const float gv = __ldcg(g + at);
-    if (gv != 0.0f) {
-      const float a = __ldcg(acc + at) + gv * gv;
-      acc[at] = a;
-      p[at] = __ldcg(p + at) - lr * gv / (sqrtf(a) + eps);
-      g[at] = 0.0f;
-    }
-  }
-}
-
 template <int DPL>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     k_hg2v_epoch(const TrainArgs a) {
