@@ -196,10 +196,8 @@ struct Mt19937 {
   // The draws of a Fisher-Yates shuffle of n items in the order they are consumed: out[q] =
   // interval(n - 1 - q) for q = 0 .. n - 2, by the same branch-free filter; the bound (and, at
   // powers of two, the mask) shrinks by one with every accepted output.  Where the bound is far
-  // from the next power of two, 16 words are decided at once (AVX-512): word p of a block is
-  // accepted for sure if it is <= bound - p (at most p outputs were accepted before it) and
-  // rejected for sure if it is > bound; a block with a word in between is left to the scalar
-  // filter.  Same stream, same results -- only faster on long rows.
+  // from the next power of two, 16 words are decided at once (AVX-512, filter16 below).  Same
+  // stream, same results -- only faster on long rows.
   void shuffle_draws(uint32_t n, uint32_t* out) {
     if (n < 2) return;
     static const bool wide = __builtin_cpu_supports("avx512f");
@@ -211,7 +209,6 @@ struct Mt19937 {
       if (wide) {
         while (p + 16 <= 1248 && i >= (mask >> 1) + 16) {
           const int c = filter16(tempered + p, mask, i, out + q);
-          if (c < 0) break;
           p += 16;
           q += (size_t)c;
           i -= (uint32_t)c;
@@ -232,17 +229,28 @@ struct Mt19937 {
   }
 
   // 16 tempered words against bound i with a constant mask: number accepted (their masked values
-  // appended to out), or -1 when a word cannot be decided without the ones before it.
+  // appended to out).  Word p is accepted for sure if it is <= i - p and rejected for sure if it
+  // is > i; the few words in between are resolved in lane order from the accept mask built so
+  // far (bound of lane p = i - number of accepted lanes before p).
   __attribute__((target("avx512f"))) static int filter16(const uint32_t* w, uint32_t mask, uint32_t i,
                                                          uint32_t* out) {
     const __m512i v = _mm512_and_si512(_mm512_loadu_si512(w), _mm512_set1_epi32((int)mask));
     const __m512i lane = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
     const __m512i top = _mm512_set1_epi32((int)i);
-    const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_sub_epi32(top, lane));
-    const __mmask16 maybe = _mm512_cmple_epu32_mask(v, top);
-    if (sure != maybe) return -1;
-    _mm512_storeu_si512(out, _mm512_maskz_compress_epi32(sure, v));
-    return __builtin_popcount((unsigned)sure);
+    unsigned acc = _mm512_cmple_epu32_mask(v, _mm512_sub_epi32(top, lane));
+    unsigned open = (unsigned)_mm512_cmple_epu32_mask(v, top) & ~acc;
+    if (open) {
+      alignas(64) uint32_t vv[16];
+      _mm512_store_si512(vv, v);
+      while (open) {
+        const int p = __builtin_ctz(open);
+        open &= open - 1;
+        const uint32_t before = (uint32_t)__builtin_popcount(acc & ((1u << p) - 1u));
+        if (vv[p] <= i - before) acc |= 1u << p;
+      }
+    }
+    _mm512_storeu_si512(out, _mm512_maskz_compress_epi32((__mmask16)acc, v));
+    return __builtin_popcount(acc);
   }
 };
 
