@@ -23,7 +23,9 @@ reference makes, and the CUDA trainer is checked against THIS restatement:
              (embedding.py:289-299)
 
 Everything is float64 here except where noted, so it is also the accuracy yardstick for the fp32
-kernels.
+kernels.  The restatement is itself checked two independent ways in tests/test_hg2v_host.py:
+finite differences of the loss, and the same model written with torch ops + autograd +
+torch.optim.Adagrad(lr=0.01, eps=1e-7), which it matches to 1e-12 over several batches.
 """
 import numpy as np
 

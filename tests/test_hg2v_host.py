@@ -132,3 +132,45 @@ def test_skeleton_wiring(monkeypatch):
   assert list(emb.node[10].values) == [1, 1] and list(emb.edge[8].values) == [2, 2]
   assert sorted(embedding.EMBEDDING_OPTIONS) == ["ALG_DIST", "HG2V_ADJ_JAC", "HG2V_ALG_DIST",
                                                  "HG2V_BOOLEAN", "HG2V_NEIGH_JAC"]
+
+
+@pytest.mark.parametrize("activation,loss", [("sigmoid", "kld"), ("relu", "mse")])
+def test_restatement_equals_torch_autograd_with_torch_adagrad(activation, loss):
+  """An independent derivation of the same training step: the model written with torch ops,
+  gradients from autograd, torch.optim.Adagrad(lr=0.01, eps=1e-7, initial accumulator 0) -- the
+  update rule Keras' Adagrad has -- over several batches with duplicated rows."""
+  import torch
+  k = 2
+  N0, E0, feats, targets = _problem(7, nodes=15, edges=9, k=k, m=96)
+  N, E = N0.copy(), E0.copy()
+  accN, accE = np.zeros_like(N), np.zeros_like(E)
+  tN = torch.tensor(N0, dtype=torch.float64, requires_grad=True)
+  tE = torch.tensor(E0, dtype=torch.float64, requires_grad=True)
+  opt = torch.optim.Adagrad([tN, tE], lr=0.01, eps=1e-7, initial_accumulator_value=0.0)
+  act = torch.sigmoid if activation == "sigmoid" else torch.relu
+
+  def loss_fn(p, y):
+    if loss == "kld":
+      yc, pc = y.clamp(1e-7, 1.0), p.clamp(1e-7, 1.0)
+      return (yc * torch.log(yc / pc)).mean()
+    return ((p - y)**2).mean()
+
+  for lo in range(0, 96, 32):
+    sel = slice(lo, lo + 32)
+    f = [np.asarray(c[sel]) for c in feats]
+    t = [np.asarray(c[sel]) for c in targets]
+    want_loss = ref.batch_step(N, E, accN, accE, f, t, k, activation, loss)
+    ft = [torch.as_tensor(c, dtype=torch.long) for c in f]
+    tt = [torch.as_tensor(c, dtype=torch.float64) for c in t]
+    Ln, Le, Rn, Re = tN[ft[0]], tE[ft[1]], tN[ft[2]], tE[ft[3]]
+    p_nn, p_ee = act((Ln * Rn).sum(1)), act((Le * Re).sum(1))
+    a = torch.stack([act((tN[ft[4 + i]] * Ln).sum(1)) for i in range(k)], 1).mean(1)
+    b = torch.stack([act((tE[ft[4 + k + i]] * Re).sum(1)) for i in range(k)], 1).mean(1)
+    total = loss_fn(p_nn, tt[0]) + loss_fn(p_ee, tt[1]) + loss_fn(a * b, tt[2])
+    opt.zero_grad()
+    total.backward()
+    opt.step()
+    assert abs(float(total.detach()) - want_loss) < 1e-12
+    assert np.abs(tN.detach().numpy() - N).max() < 1e-12
+    assert np.abs(tE.detach().numpy() - E).max() < 1e-12
+  assert np.abs(N - N0).max() > 1e-3
