@@ -140,3 +140,47 @@ def test_compress_range_invariants():
   back_e = {(inv_node[n], inv_edge[e]) for e, d in compressed.edge.items() for n in d.nodes}
   assert back_e == back
   assert not hg.node[4].HasField("weight")      # the input is not mutated
+
+
+# ---- tests/test_hypergraph_util.py:39-86, 131-179 of the reference, restated -----------------
+
+
+def test_add_node_to_edge_typical_dupl_and_names():
+  actual = Hypergraph()
+  AddNodeToEdge(actual, 1, 2)
+  AddNodeToEdge(actual, 1, 2)                      # duplicate calls do not change the structure
+  expected = Hypergraph()
+  expected.node[1].edges.append(2)
+  expected.edge[2].nodes.append(1)
+  assert actual == expected
+
+  actual = Hypergraph()
+  AddNodeToEdge(actual, 0, 0, "A", "X")
+  AddNodeToEdge(actual, 1, 0, node_name="B")
+  AddNodeToEdge(actual, 1, 1, edge_name="Y")
+  expected = Hypergraph()
+  expected.node[0].edges.append(0)
+  expected.node[0].name = "A"
+  expected.node[1].edges.extend([0, 1])
+  expected.node[1].name = "B"
+  expected.edge[0].nodes.extend([0, 1])
+  expected.edge[0].name = "X"
+  expected.edge[1].nodes.append(1)
+  expected.edge[1].name = "Y"
+  assert actual == expected
+
+
+def test_to_csr_matrix_one_multiple_and_empty():
+  one = Hypergraph()
+  AddNodeToEdge(one, 1, 2)
+  assert np.array_equal(ToCsrMatrix(one).toarray(), [[0, 0, 0], [0, 0, 1]])
+  assert np.array_equal(ToEdgeCsrMatrix(one).toarray(), [[0, 0], [0, 0], [0, 1]])
+  multiple = Hypergraph()
+  AddNodeToEdge(multiple, 1, 1)
+  AddNodeToEdge(multiple, 1, 2)
+  AddNodeToEdge(multiple, 2, 0)
+  assert np.array_equal(ToCsrMatrix(multiple).toarray(), [[0, 0, 0], [0, 1, 1], [1, 0, 0]])
+  assert ToCsrMatrix(multiple).dtype == bool
+  empty = ToCsrMatrix(Hypergraph())
+  assert empty.shape == sps.csr_matrix([]).shape and empty.nnz == 0
+  assert ToEdgeCsrMatrix(Hypergraph()).nnz == 0
