@@ -95,6 +95,46 @@ def algorithmic_bytes_per_sweep(N, E, nnz, R):
   return 2 * nnz * (4 * R + 4) + 2 * (N + E) * 4 * R
 
 
+def compulsory_bytes_per_launch(N, E, nnz, R):
+  """DRAM bytes a half-sweep cannot avoid, averaged over the two halves:
+  one 4-byte stream slot per incidence, every owned row read and written once, and the gathered
+  table read from DRAM once (it was written by the previous launch and does not fit L2 next to
+  the streamed data).  The algorithmic figure counts the gathered row once per INCIDENCE
+  instead -- the difference is what L2 serves."""
+  return (2 * nnz * 4 + 3 * (N + E) * 4 * R) / 2.0
+
+
+def kernel_source_sha():
+  """Hash of the CUDA sources: an ncu capture is only quoted next to the kernels it measured."""
+  import glob
+  import hashlib
+  h = hashlib.sha256()
+  for path in sorted(glob.glob(os.path.join(ROOT, "hypergraphembedding_b200", "csrc", "*.cu*"))):
+    h.update(open(path, "rb").read())
+  return h.hexdigest()[:16]
+
+
+def parity_against(A, xn, xe, ref_xn, ref_xe, R):
+  """The north-star bar on a relaxation result: distance of every stored incidence against the
+  reference arithmetic (f64), |d - d_ref| <= 1e-5 d_ref + 1e-6 sqrt(R); HOBE incidence weights
+  (sqrt(R) - d) / sqrt(R) alongside.  Returns the worst ratio to the bound (<= 1 passes)."""
+  A = A.tocoo()
+  worst = worst_abs = 0.0
+  step = 1 << 20
+  for i in range(0, A.nnz, step):
+    r, c = A.row[i:i + step], A.col[i:i + step]
+    d = np.sqrt(((xn[r].astype(np.float64) - xe[c].astype(np.float64))**2).sum(axis=1))
+    dr = np.sqrt(((ref_xn[r].astype(np.float64) - ref_xe[c].astype(np.float64))**2).sum(axis=1))
+    err = np.abs(d - dr)
+    worst = max(worst, float((err / (1e-5 * dr + 1e-6 * np.sqrt(R))).max()))
+    worst_abs = max(worst_abs, float(err.max()))
+  coord = max(float(np.abs(xn - ref_xn).max()), float(np.abs(xe - ref_xe).max()))
+  return {"max_dist_err_over_bound": worst, "max_dist_abs_err": worst_abs,
+          "max_weight_err": worst_abs / float(np.sqrt(R)), "max_coord_abs_err": coord,
+          "n_incidences": int(A.nnz), "bound": "|d - d_ref| <= 1e-5 d_ref + 1e-6 sqrt(R)",
+          "ok": bool(worst <= 1.0)}
+
+
 def hbm_peak():
   path = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(path):
@@ -105,15 +145,19 @@ def hbm_peak():
   return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the half-sweep kernel from the
-  committed `ncu --set full` capture (profiles/half_sweep_traffic.json, written by
-  tools/ncu_summary.py); None when there is no capture of this workload."""
-  path = os.path.join(ROOT, "profiles", "half_sweep_traffic.json")
+def ncu_traffic(workload, key="half_sweep"):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the
+  committed `ncu --set full` capture (profiles/<key>_traffic.json, written by
+  tools/ncu_traffic.py).  None when there is no capture of this workload, or when the capture
+  was taken from other kernel sources than the ones in this tree (the file carries their hash)."""
+  path = os.path.join(ROOT, "profiles", key + "_traffic.json")
   try:
     d = json.load(open(path))
-    if d.get("workload") == workload:
-      return float(d["bytes_per_launch"]), d.get("source")
+    if d.get("workload") != workload:
+      return None, None
+    if d.get("kernel_source_sha") != kernel_source_sha():
+      return None, "stale: %s was captured from other kernel sources" % os.path.relpath(path, ROOT)
+    return float(d["bytes_per_launch"]), d.get("source")
   except (OSError, ValueError, KeyError):
     pass
   return None, None
@@ -188,18 +232,21 @@ class ClockSampler(object):
             "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_port(A, B, spec, sweeps, threads=0):
+def cpu_baseline_port(A, B, spec, sweeps, threads=0, keep=None):
   """The oracle port (oracle/algdist_ref.c: the reference's per-row f64 arithmetic, rows spread
   over all host cores the way the reference spreads them over a process pool) on `sweeps`
-  sweeps of the full workload.  Returns (nnz*R*iters/s, seconds, threads)."""
+  sweeps of the full workload.  Returns (nnz*R*iters/s, seconds, threads); the relaxed vectors
+  are appended to `keep` when given (bench.py checks the GPU result against them)."""
   from hypergraphembedding_b200 import synthetic
   from oracle import cport
   xn0, xe0 = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], spec["R"], seed=0)
   xn0, xe0 = xn0.astype(np.float64), xe0.astype(np.float64)
   cport.load()
   t = time.time()
-  cport.algdist(A, B, xn0, xe0, sweeps, threads=threads)
+  result = cport.algdist(A, B, xn0, xe0, sweeps, threads=threads)
   dt = time.time() - t
+  if keep is not None:
+    keep.extend(result)
   return A.nnz * spec["R"] * sweeps / dt, dt, (threads or cport.max_threads())
 
 
@@ -533,6 +580,7 @@ def run_ours(args, spec):
   launches = ctx.launch_count - launches0
   ms_per_step = total_ms / args.steps
   value = nnz * R * sweeps / (ms_per_step * 1e-3)
+  gpu_xn, gpu_xe = xn.cpu().numpy(), xe.cpu().numpy()      # result of the last timed step
 
   # ---- per-launch duration of the half-sweep kernel (stepwise API, same stream) -------------
   st = _native.AlgDistState(ctx, inc, R, sweeps)
@@ -596,17 +644,27 @@ def run_ours(args, spec):
   d2h = (h_xn.numel() + h_xe.numel()) * 4
 
 
+  # the C port runs the full workload from the same seed-0 vectors: it is the CPU baseline AND the
+  # checker of the device arm's result (full-size parity on the headline configuration)
   cpu_sweeps = sweeps
-  cpu_value, cpu_dt, cpu_threads = cpu_baseline_port(A, B, spec, cpu_sweeps)
+  ref = []
+  cpu_value, cpu_dt, cpu_threads = cpu_baseline_port(A, B, spec, cpu_sweeps, keep=ref)
+  parity = parity_against(A, gpu_xn, gpu_xe, ref[0], ref[1], R)
+  parity["against"] = "oracle/algdist_ref.c (f64, the reference's per-row arithmetic), full workload, %d sweeps" % sweeps
+  del ref
   try:
     scipy_line = cpu_baseline_scipy(A, B, spec)
   except Exception as exc:
     scipy_line = {"error": "%s: %s" % (type(exc).__name__, exc)}
   extras = {}
   if not args.no_extras:
+    inc.close()
+    del a_ptr, a_idx, b_ptr, b_idx, xn, xe, xn_init, xe_init
+    torch.cuda.empty_cache()
     for key, fn in (("hobe", hobe_extra), ("hg2v_train", hg2v_train_extra),
                     ("c1_end_to_end", c1_end_to_end_extra),
-                    ("pair_weighting", pair_weighting_extra)):
+                    ("pair_weighting", pair_weighting_extra),
+                    ("c5", lambda c: c5_extra(args, 1, 0, local_rank, c))):
       try:
         extras[key] = fn(ctx)
       except Exception as exc:   # the headline line must survive a failing side measurement
@@ -622,12 +680,21 @@ def run_ours(args, spec):
                  "l2": "no flush: per-step working set (vectors %d MB + incidence %d MB) exceeds the 126 MB L2"
                        % ((N + E) * R * 4 >> 20, (2 * nnz * 4) >> 20),
                  "device_vs_host_arm_identical": same},
-      "roofline": {"bound": "hbm", "kernel": "k_half_sweep<8>", "achieved": achieved, "peak": peak,
+      "parity": parity,
+      "roofline": {"bound": "hbm", "kernel": "k_sweep<8, node | edge>", "achieved": achieved, "peak": peak,
                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                    "traffic_source": traffic_src, "peak_source": peak_src,
                    "bytes_per_launch": bytes_per_launch, "ms_per_launch": mean_half_ms,
                    "node_half_ms": node_ms, "edge_half_ms": edge_ms,
-                   "frac_of_nominal_8TBs": achieved / 8000.0},
+                   "frac_of_nominal_8TBs": achieved / 8000.0,
+                   # `achieved` counts one gathered row per INCIDENCE, most of which L2
+                   # serves; the DRAM side of the same launch:
+                   "dram_GBps": traffic / (mean_half_ms * 1e-3) / 1e9 if traffic else None,
+                   "dram_frac": traffic / (mean_half_ms * 1e-3) / 1e9 / peak if traffic else None,
+                   "compulsory_bytes_per_launch": compulsory_bytes_per_launch(N, E, nnz, R),
+                   "compulsory_GBps": compulsory_bytes_per_launch(N, E, nnz, R) / (mean_half_ms * 1e-3) / 1e9,
+                   "compulsory_frac": compulsory_bytes_per_launch(N, E, nnz, R) / (mean_half_ms * 1e-3) / 1e9 / peak,
+                   "kernel_source_sha": kernel_source_sha()},
       "cpu_baseline": {"value": cpu_value, "unit": "nnz*R*iters/s", "cores": cpu_threads,
                        "kind": "port",
                        "sample": "the full workload, %d of %d sweeps, C restatement of the reference's "
@@ -641,6 +708,9 @@ def run_ours(args, spec):
   }
   out.update(extras)
   print(json.dumps(out), flush=True)
+  if not parity["ok"]:
+    log("PARITY FAILED: %s" % json.dumps(parity))
+    sys.exit(1)
 
 
 def community_shard_device(spec, rank, world, device):
@@ -692,19 +762,18 @@ def community_shard_device(spec, rank, world, device):
               nnz=int(a_idx.numel()))
 
 
-def run_community(args, spec, world, rank, local_rank):
-  """--workload c5 / c5mini: strong scaling of one fixed hypergraph over the ranks (N = 1: the
-  plain single-GPU path).  Device-resident arm only."""
+def community_measure(spec, world, rank, local_rank, ctx, steps, warmup, comm="auto", slices=1,
+                      oracle_check=False, force_tiles=False):
+  """One strong-scaling measurement of a config-5-family hypergraph over `world` ranks (1: the
+  plain single-GPU path).  The process group must be up when world > 1.  Returns a dict on every
+  rank.  oracle_check: the blocks and the result are gathered on rank 0 and compared with the C
+  port of the reference arithmetic (small members of the family only)."""
   import torch
   import torch.distributed as dist
   from hypergraphembedding_b200 import _native
   from hypergraphembedding_b200 import distributed as hd
 
-  torch.cuda.set_device(local_rank)
   device = torch.device("cuda", local_rank)
-  if world > 1:
-    init_process_group_quiet(rank, world, device)
-  ctx = _native.default_context(local_rank)
   t = time.time()
   g = community_shard_device(spec, rank, world, device)
   torch.cuda.synchronize()
@@ -720,38 +789,38 @@ def run_community(args, spec, world, rank, local_rank):
   gen.manual_seed(10**6)
   xe_init = torch.rand((E, R), device=device, generator=gen)       # identical on every rank
   xn, xe = torch.empty_like(xn_init), torch.empty_like(xe_init)
+  if force_tiles:
+    ctx.set_tile_mb(8, 0)     # node-range tiles of 8 MB whatever the sizes (the config-5 code path)
 
   if world == 1:
     inc = _native.Incidence(ctx, n_loc, E, g["a_ptr"], g["a_idx"], g["b_ptr"], g["b_idx"])
-    relax, comm = None, "single GPU"
+    relax, exchange = None, "single GPU"
 
     def step():
       xn.copy_(xn_init)
       xe.copy_(xe_init)
       _native.algdist_run(ctx, inc, xn, xe, sweeps)
   else:
-    relax = hd.ShardedRelaxation(None, R, sweeps, comm=args.comm, num_slices=args.slices, ctx=ctx,
+    inc = None
+    relax = hd.ShardedRelaxation(None, R, sweeps, comm=comm, num_slices=slices, ctx=ctx,
                                  shape=(n_loc, E),
                                  csr_device=(g["a_ptr"], g["a_idx"], g["b_ptr"], g["b_idx"]))
-    comm = "p2p" if relax.use_p2p else "nccl"
+    exchange = "p2p" if relax.use_p2p else "nccl"
 
     def step():
       xn.copy_(xn_init)
       xe.copy_(xe_init)
       relax.run(xn, xe)
 
-  for _ in range(args.warmup):
+  for _ in range(warmup):
     step()
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
   launches0 = ctx.launch_count
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
   ev0.record()
-  for _ in range(args.steps):
+  for _ in range(steps):
     step()
   ev1.record()
   torch.cuda.synchronize()
@@ -759,40 +828,177 @@ def run_community(args, spec, world, rank, local_rank):
   if world > 1:
     dist.barrier()
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-  ms_per_step = float(ms.item()) / args.steps
+  ms_per_step = float(ms.item()) / steps
   launches = ctx.launch_count - launches0
-  clocks = sampler.stop() if rank == 0 else None
-  value = nnz_global * R * sweeps / (ms_per_step * 1e-3)
-  N = spec["num_nodes"]
-  bytes_step = algorithmic_bytes_per_sweep(N, E, nnz_global, R) * sweeps
-  achieved = bytes_step / (ms_per_step * 1e-3) / 1e9 / world      # per GPU, whole step
-  peak, peak_src = hbm_peak()
   finite = bool(torch.isfinite(xn).all().item() and torch.isfinite(xe).all().item())
   span_ok = bool((xe.min() >= -1e-6).item() and (xe.max() <= 1 + 1e-6).item())
+  out = {"ms_per_step": ms_per_step, "value": nnz_global * R * sweeps / (ms_per_step * 1e-3),
+         "nnz": nnz_global, "nnz_per_gpu": g["nnz"], "n_loc": n_loc, "E": E, "exchange": exchange,
+         "generate_s": gen_s, "launches": int(launches) * world, "result_finite": finite,
+         "result_in_unit_cube": span_ok,
+         "tiled": bool(force_tiles or n_loc * R * 4 > (512 << 20)), "parity": None}
+
+  if oracle_check:
+    block = [t.cpu().numpy() for t in (g["a_ptr"], g["a_idx"], xn_init, xn)]
+    blocks = [None] * world
+    if world > 1:
+      dist.gather_object(block, blocks if rank == 0 else None, dst=0)
+    else:
+      blocks = [block]
+    if rank == 0:
+      import scipy.sparse as sps
+      from oracle import cport
+      A = sps.vstack([sps.csr_matrix((np.ones(len(b[1]), dtype=bool), b[1], b[0]),
+                                     shape=(len(b[0]) - 1, E)) for b in blocks]).tocsr()
+      A.sort_indices()
+      B = A.T.tocsr()
+      B.sort_indices()
+      x0 = np.concatenate([b[2] for b in blocks]).astype(np.float64)
+      ref_xn, ref_xe = cport.algdist(A, B, x0, xe_init.cpu().numpy().astype(np.float64), sweeps)
+      out["parity"] = parity_against(A, np.concatenate([b[3] for b in blocks]), xe.cpu().numpy(),
+                                     ref_xn, ref_xe, R)
+      out["parity"]["against"] = "oracle/algdist_ref.c (f64) on the gathered blocks, %d sweeps" % sweeps
+
   if relax is not None:
     relax.close()
+  if inc is not None:
+    inc.close()
+  if force_tiles:
+    ctx.set_tile_mb(64, 512)
+  del g, xn_init, xe_init, xn, xe
+  torch.cuda.empty_cache()
+  return out
+
+
+def c5_extra(args, world, rank, local_rank, ctx):
+  """BASELINE.json configs[4] inside the driver-run lines: (1) the 1/100-scale member of the family
+  sharded over the ranks and checked against the oracle, untiled and with node-range tiles forced
+  (the code path the full size takes); (2) the full 65M-node / 1.8B-incidence hypergraph
+  strong-scaled over the ranks; (3) at N > 1, the same hypergraph on rank 0's GPU alone, so the
+  speed-up is measured inside one run on one box."""
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import distributed as hd
+  mini, full = WORKLOADS["c5mini"], WORKLOADS["c5"]
+  out = {"workload": full["name"]}
+  checks = []
+  for tiles in (False, True):
+    m = community_measure(mini, world, rank, local_rank, ctx, 1, 1, comm=args.comm, slices=args.slices,
+                          oracle_check=True, force_tiles=tiles)
+    if world > 1:
+      hd.release_peer_arenas(dist)
+    if rank == 0:
+      checks.append(dict(m["parity"], tiled=tiles, nnz=m["nnz"], exchange=m["exchange"]))
+  out["c5mini_parity"] = checks
+  m = community_measure(full, world, rank, local_rank, ctx, max(1, min(args.steps, 3)), 1, comm=args.comm,
+                        slices=args.slices)
+  if world > 1:
+    hd.release_peer_arenas(dist)
+  out.update({k: m[k] for k in ("ms_per_step", "value", "nnz", "nnz_per_gpu", "exchange", "tiled",
+                                "result_finite", "result_in_unit_cube", "generate_s")})
+  out["n_gpus"] = world
+  if world > 1:
+    one = None
+    if rank == 0:
+      one = community_measure(full, 1, 0, local_rank, ctx, 2, 1)
+    dist.barrier()
+    if rank == 0:
+      out["n1_ms_per_step"] = one["ms_per_step"]
+      out["n1_value"] = one["value"]
+      out["speedup_vs_c5_n1"] = one["ms_per_step"] / m["ms_per_step"]
+      out["n1_note"] = "the same hypergraph family member on rank 0's GPU alone, measured in this run"
+  return out if rank == 0 else None
+
+
+def run_community(args, spec, world, rank, local_rank):
+  """--workload c5 / c5mini: strong scaling of one fixed hypergraph over the ranks (N = 1: the
+  plain single-GPU path).  Device-resident arm only."""
+  import torch
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import _native
+  from hypergraphembedding_b200 import distributed as hd
+
+  torch.cuda.set_device(local_rank)
+  device = torch.device("cuda", local_rank)
+  if world > 1:
+    init_process_group_quiet(rank, world, device)
+  ctx = _native.default_context(local_rank)
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  m = community_measure(spec, world, rank, local_rank, ctx, args.steps, args.warmup, comm=args.comm,
+                        slices=args.slices, oracle_check=spec["num_nodes"] <= 1000000)
+  clocks = sampler.stop() if rank == 0 else None
+  N, E, R, sweeps = spec["num_nodes"], m["E"], spec["R"], spec["sweeps"]
+  bytes_step = algorithmic_bytes_per_sweep(N, E, m["nnz"], R) * sweeps
+  achieved = bytes_step / (m["ms_per_step"] * 1e-3) / 1e9 / world      # per GPU, whole step
+  peak, peak_src = hbm_peak()
   if rank == 0:
     out = {
-        "metric": "alg-dist incidence nnz*R*iters/sec", "value": value, "unit": "nnz*R*iters/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "metric": "alg-dist incidence nnz*R*iters/sec", "value": m["value"], "unit": "nnz*R*iters/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": spec["name"], "nodes": N, "edges": E, "nnz": nnz_global,
-                   "nnz_per_gpu": g["nnz"], "R": R, "sweeps": sweeps, "seed": spec["seed"],
-                   "exchange": comm, "generate_s": gen_s, "result_finite": finite,
-                   "result_in_unit_cube": span_ok,
+        "config": {"workload": spec["name"], "nodes": N, "edges": E, "nnz": m["nnz"],
+                   "nnz_per_gpu": m["nnz_per_gpu"], "R": R, "sweeps": sweeps, "seed": spec["seed"],
+                   "exchange": m["exchange"], "generate_s": m["generate_s"],
+                   "result_finite": m["result_finite"], "result_in_unit_cube": m["result_in_unit_cube"],
                    "l2": "no flush: per-GPU working set exceeds the 126 MB L2"},
+        "parity": m["parity"],
         "roofline": {"bound": "hbm", "kernel": "whole step (load + %d sweeps + store), per GPU" % sweeps,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": bytes_step / world, "ms_per_launch": ms_per_step},
+                     "bytes_per_launch": bytes_step / world, "ms_per_launch": m["ms_per_step"]},
         "cpu_baseline": None, "e2e": None,
-        "gpu_launches": int(launches) * world, "clocks": clocks,
+        "gpu_launches": m["launches"], "clocks": clocks,
     }
     print(json.dumps(out), flush=True)
   if world > 1:
     hd.release_peer_arenas(dist)
     dist.destroy_process_group()
+
+
+def sharded_parity_check(world, rank, ctx, comm, slices, R=32, iters=10):
+  """The multi-rank relaxation against the oracle before anything is timed: a 80 000-node /
+  3 000-edge / ~0.98M-incidence hypergraph (the case of tests/check_multi_gpu_parity.py), node
+  rows sharded over the ranks by incidence count, `iters` sweeps; the blocks are gathered on
+  rank 0 and compared with oracle/port.py (scipy f64)."""
+  import torch
+  import torch.distributed as dist
+  import scipy.sparse as sps
+  from hypergraphembedding_b200 import distributed as hd
+  n, e, nnz = 80000, 3001, 900000
+  rng = np.random.default_rng(21)
+  rows = np.concatenate([rng.integers(0, n, nnz), np.arange(n), rng.integers(0, n, e)])
+  cols = np.concatenate([rng.integers(0, e, nnz), rng.integers(0, e, n), np.arange(e)])
+  A = sps.csr_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=(n, e), dtype=bool)
+  A.sum_duplicates()
+  A.sort_indices()
+  rng = np.random.default_rng(123)
+  xn0 = rng.random((n, R)).astype(np.float32)
+  xe0 = rng.random((e, R)).astype(np.float32)
+  A_loc, r0, r1 = hd.local_shard(A, rank, world)
+  relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices, comm=comm, ctx=ctx)
+  xn = torch.from_numpy(xn0[r0:r1].copy()).cuda()
+  xe = torch.from_numpy(xe0.copy()).cuda()
+  relax.run(xn, xe)
+  torch.cuda.synchronize()
+  exchange = "p2p" if relax.use_p2p else "nccl"
+  relax.close()
+  hd.release_peer_arenas(dist)
+  blocks = [None] * world
+  dist.gather_object((r0, r1, xn.cpu().numpy()), blocks if rank == 0 else None, dst=0)
+  if rank != 0:
+    return None
+  from oracle import port
+  ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, iters)
+  got = np.zeros_like(xn0)
+  for b0, b1, blk in blocks:
+    got[b0:b1] = blk
+  res = parity_against(A, got, xe.cpu().numpy(), ref_xn, ref_xe, R)
+  res.update(case="80000 nodes / 3001 edges / %d incidences, R=%d, %d sweeps, %d ranks (%s) vs oracle/port.py"
+                  % (A.nnz, R, iters, world, exchange))
+  return res
 
 
 def run_sharded(args, spec, world, rank, local_rank):
@@ -808,6 +1014,9 @@ def run_sharded(args, spec, world, rank, local_rank):
   ctx = _native.default_context(local_rank)
   if os.environ.get("HGE_BLOCKS_PER_SM"):
     ctx.set_tuning(0, 0, int(os.environ["HGE_BLOCKS_PER_SM"]))
+  parity = sharded_parity_check(world, rank, ctx, args.comm, args.slices)
+  if rank == 0:
+    log("multi-rank parity: %s" % json.dumps(parity))
   shard_spec = dict(spec, seed=spec["seed"] + rank)
   A, B = build_workload(shard_spec)
   n_loc, E = A.shape
@@ -912,6 +1121,15 @@ def run_sharded(args, spec, world, rank, local_rank):
       (xn0.size + xe0.size) * 4 + E * 8
   d2h = (xn0.size + xe0.size) * 4
   relax.close()
+  hd.release_peer_arenas(dist)
+  del xn, xe, xn_init, xe_init
+  torch.cuda.empty_cache()
+  c5 = None
+  if not args.no_extras:
+    try:
+      c5 = c5_extra(args, world, rank, local_rank, ctx)
+    except Exception as exc:       # every rank fails or none does (same shapes, same memory)
+      c5 = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
   if rank == 0:
     out = {
@@ -940,10 +1158,15 @@ def run_sharded(args, spec, world, rank, local_rank):
                 "d2h_bytes_per_step": int(d2h) * world},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
+        "parity": parity,
+        "c5": c5,
     }
     print(json.dumps(out), flush=True)
+  ok = parity is None or parity["ok"]
   hd.release_peer_arenas(dist)
   dist.destroy_process_group()
+  if not ok:
+    sys.exit(1)
 
 
 def main():

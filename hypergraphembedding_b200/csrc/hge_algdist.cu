@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "hge_incidence.cuh"
+#include "hge_sweep.cuh"
 
 namespace {
 
@@ -259,7 +260,6 @@ struct HalfSweepArgs {
   float4* const* push_stage;
   int32_t push_rows;
   int32_t push_rank;
-  int32_t skip_heavy;          // 1: the long rows are gathered by k_heavy_bulk instead
   int32_t R;
   int32_t ld4;
 };
@@ -570,9 +570,8 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
   // ---- long rows: one warp per chunk of the row --------------------------------------
   // Loads are software-pipelined: the descriptor of the next chunk and the next block of 32
   // column ids are requested before the current block's rows are consumed, so a warp pays
-  // one memory latency per block of 32 gathered rows.  (Skipped when the bulk-copy kernel
-  // below has taken the long rows.)
-  if (!a.skip_heavy) {
+  // one memory latency per block of 32 gathered rows.
+  {
     int2 ch_next = make_int2(0, 0);
     if (gw < a.n_chunks) ch_next = __ldcs(a.chunks + gw);
     for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
@@ -681,144 +680,6 @@ __global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const Hal
   own.template publish_minmax<kWarps>(smin, smax);
 }
 
-// ----------------------------------------------------------------------------------------
-// long rows through the bulk-copy engine (TMA, non-tensor form)
-// ----------------------------------------------------------------------------------------
-// The register-based gather above can keep at most (resident warps x 8 x 512 B) in flight per
-// SM, bounded by the register file.  Here every lane hands one gathered row to the bulk-copy
-// engine (cp.async.bulk global -> shared, completion counted on an mbarrier): a warp-wide
-// instruction requests 32 rows, the rows land in a per-warp ring of STAGES x 32 row buffers in
-// shared memory, and the warp only reads them back (conflict-free LDS.128) to add them up.
-// In flight per SM: WARPS x (STAGES - 1) x 32 rows, bounded by the 227 KB of shared memory
-// instead of registers.
-// MEASURED (profiles/r1_bulk_copy_experiment.md): slower than the register gather for 128-byte
-// rows -- UBLKCP takes uniform-register operands, so the 32 per-lane copies of a warp are
-// issued one after the other, and the copy engine sustains about one 128-byte request per
-// ~40 cycles per SM.  Config 2: 0.607 vs 0.478 ms per sweep; config 5 on one GPU: 6.0 vs
-// 2.9 s per step.  Kept as an opt-in (hge_ctx_set_bulk) for wide rows; off by default.
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_row_g2s(void* dst, const void* src, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-template <int LPR, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_heavy_bulk(const HalfSweepArgs a) {
-  constexpr int G = 32 / LPR;
-  constexpr int ROW4 = LPR;                          // float4 slots per staged row
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-#if HGE_SMEM_STATE
-  __shared__ float4 s_state_bulk[4 * WARPS * 32];
-  RowOwner<LPR> own(a, s_state_bulk, WARPS * 32);
-#else
-  RowOwner<LPR> own(a);
-#endif
-  const int lane = own.lane, gl = own.gl, g = own.g, ld4 = own.ld4;
-  const bool active = own.active, raw_out = own.raw_out;
-  float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)own.warp * STAGES * 32 * ROW4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * STAGES * 32 * ROW4 * 16) +
-                   own.warp * STAGES;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int row_f4 = min(LPR, ld4 - own.slab * LPR);   // float4 of a row in this column slab
-  const uint32_t row_bytes = (uint32_t)row_f4 * 16u;
-  uint32_t parity = 0;                                 // bit s: phase of stage s
-  const int64_t gw = (int64_t)blockIdx.x * WARPS + own.warp;
-  const int64_t nw = (int64_t)gridDim.x * WARPS;
-
-  for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
-    const int2 ch = a.chunks[ci];
-    const HgeHeavyRow hr = a.hrows[ch.x];
-    const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
-    const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
-    const int32_t* cidx = a.idx + start;
-    const int nblk = (count + 31) >> 5;
-    float4 yown = hge_f4_zero();
-    if (hr.nchunks == 1 && g == 0 && active && !raw_out) yown = own.load_own(hr.row);
-
-    // hand block b (32 incidences) to the copy engine; `col` is this lane's column id of it
-    auto issue = [&](int b, int col) {
-      const int s = b % STAGES;
-      const int valid = min(32, count - b * 32);
-      if (lane == 0) mbar_expect_tx(bars + s, (uint32_t)valid * row_bytes);
-      __syncwarp();
-      if (col >= 0)
-        bulk_row_g2s(ring + ((size_t)s * 32 + lane) * ROW4,
-                     a.yg + (size_t)col * ld4 + own.slab * LPR, row_bytes, bars + s);
-    };
-    auto load_col = [&](int b) -> int {
-      return (b < nblk && b * 32 + lane < count) ? __ldcs(cidx + b * 32 + lane) : -1;
-    };
-
-    int col_next = load_col(0);
-#pragma unroll 1
-    for (int b = 0; b < STAGES - 1 && b < nblk; ++b) {
-      const int col = col_next;
-      col_next = load_col(b + 1);
-      issue(b, col);
-    }
-    float4 acc = hge_f4_zero();
-    for (int b = 0; b < nblk; ++b) {
-      const int ahead = b + STAGES - 1;
-      if (ahead < nblk) {
-        const int col = col_next;
-        col_next = load_col(ahead + 1);
-        issue(ahead, col);
-      }
-      const int s = b % STAGES;
-      mbar_wait(bars + s, (parity >> s) & 1u);
-      parity ^= 1u << s;
-      const float4* stage = ring + (size_t)s * 32 * ROW4;
-      const int valid = min(32, count - b * 32);
-#pragma unroll
-      for (int r = 0; r < LPR; ++r) {
-        const int t = r * G + g;
-        if (t < valid && active) hge_f4_add(acc, stage[(size_t)t * ROW4 + gl]);
-      }
-      __syncwarp();   // every lane has read stage s before it is handed out again
-    }
-    own.finish_chunk(hr, ch, acc, yown);
-  }
-
-  float4(*smin)[LPR] = reinterpret_cast<float4(*)[LPR]>(smem_raw);
-  float4(*smax)[LPR] = smin + WARPS;
-  __syncthreads();    // all rings are idle; reuse the front of shared memory for the reduction
-  own.template publish_minmax<WARPS>(smin, smax);
-}
-
 // Sharded edge half, second part: the raw sums have been all-reduced over the shards.
 __global__ void k_edge_finalize(int64_t row0, int64_t rows, int R, int ld,
                                 const float* __restrict__ raw,
@@ -913,34 +774,8 @@ void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays
 namespace {
 
 template <int LPR>
-struct BulkConfig {
-  static constexpr int kWarpsPerBlock = (LPR == 32) ? 4 : 8;
-  static constexpr int kStages = (LPR <= 8) ? 6 : 3;
-  static constexpr size_t kSmem =
-      (size_t)kWarpsPerBlock * kStages * 32 * LPR * 16 + (size_t)kWarpsPerBlock * kStages * 8;
-};
-
-template <int LPR>
 int launch_half(hge_algdist* st, HalfSweepArgs a) {
   hge_ctx* ctx = st->ctx;
-  a.skip_heavy = 0;
-  if (ctx->use_bulk && a.n_chunks > 0) {
-    // long rows: bulk-copy kernel, one block per SM; short rows: the register gather below
-    using Cfg = BulkConfig<LPR>;
-    auto kernel = k_heavy_bulk<LPR, Cfg::kWarpsPerBlock, Cfg::kStages>;
-    static bool configured = false;
-    if (!configured) {
-      HGE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::kSmem));
-      configured = true;
-    }
-    const int blocks = (int)std::min<int64_t>(
-        ctx->num_sms, ((int64_t)a.n_chunks + Cfg::kWarpsPerBlock - 1) / Cfg::kWarpsPerBlock);
-    kernel<<<dim3(blocks, st->slabs), Cfg::kWarpsPerBlock * 32, Cfg::kSmem, ctx->stream>>>(a);
-    HGE_CHECK_LAUNCH(ctx);
-    a.skip_heavy = 1;
-    if (a.n_light == 0) return HGE_OK;
-  }
   dim3 grid(st->grid, st->slabs);
   k_half_sweep<LPR><<<grid, kBlock, 0, ctx->stream>>>(a);
   HGE_CHECK_LAUNCH(ctx);
@@ -961,13 +796,66 @@ int occupancy_grid(const hge_ctx* ctx, int* out) {
   return HGE_OK;
 }
 
+// Blocks of the stream-fed kernel for one schedule: two waves of resident blocks (a warp owns one
+// contiguous piece; the second wave evens out what the cost model of the pieces gets wrong:
+// 0.399 -> 0.310 ms per sweep on config 2, profiles/r2_half_sweep.md), fewer when there are not
+// enough units to go round.
+int sweep_blocks(const hge_algdist* st, const HgeHalfSchedule& s, int G) {
+  const hge_ctx* ctx = st->ctx;
+  const int per_sm = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 2 * st->sweep_resident;
+  const int64_t units = (int64_t)s.n_chunks + (s.n_light + G - 1) / G;
+  const int64_t want = std::max<int64_t>(1, (units + kWarps - 1) / kWarps);
+  return (int)std::min<int64_t>((int64_t)per_sm * ctx->num_sms, want);
+}
+
+int run_half_stream(hge_algdist* st, HgeHalfSchedule& s, bool node_half, int sweep, float* raw,
+                    const hge_p2p* push, bool accumulate) {
+  hge_ctx* ctx = st->ctx;
+  const int G = 32 / st->lpr;
+  const int mode = push ? kSweepPush : raw ? (accumulate ? kSweepRawAdd : kSweepRaw)
+                                           : (node_half ? kSweepNode : kSweepEdge);
+  const int with_own = (mode == kSweepNode || mode == kSweepEdge) ? 1 : 0;
+  // the stream holds absolute rows of the allocation that starts at the edge rows (ye)
+  const int64_t yn_row = (st->yn - st->ye) / st->ld;
+  HGE_REQUIRE(st->yn >= st->ye && (st->yn - st->ye) % st->ld == 0 && yn_row + st->inc->N < 0xffffffffll,
+              "relaxation tables are not rows of one allocation");
+  const uint32_t gather0 = node_half ? 0u : (uint32_t)yn_row;
+  const uint32_t own0 = node_half ? (uint32_t)yn_row : 0u;
+  const int blocks = sweep_blocks(st, s, G);
+  HGE_TRY(hge_sched_stream(ctx, &s, G, with_own, gather0, own0, st->zero_row, blocks * kWarps));
+  const HgeStream& t = s.stream;
+  HgeSweepArgs a;
+  a.stream = t.ids;
+  a.items = t.items;
+  a.uoff = t.uoff;
+  a.piece = t.piece;
+  a.hrows = s.hrows;
+  a.chunks = s.chunks;
+  a.n_chunks = s.n_chunks;
+  a.n_hrows = s.n_hrows;
+  a.base = reinterpret_cast<const float4*>(st->ye);
+  a.own = reinterpret_cast<float4*>(node_half ? st->yn : st->ye);
+  a.partials = st->partials;
+  a.counters = st->counters;
+  a.mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
+  a.mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
+  a.raw = reinterpret_cast<float4*>(raw);
+  a.push_stage = push ? push->d_peer_stage : nullptr;
+  a.push_rows = push ? push->own_rows : 1;
+  a.push_rank = push ? push->rank : 0;
+  a.R = st->R;
+  a.ld4 = st->ld4;
+  return hge_sweep_launch(ctx, a, st->lpr, mode, blocks, st->slabs);
+}
+
 int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice = -1,
-             const hge_p2p* push = nullptr, const HgeHalfSchedule* tile = nullptr,
+             const hge_p2p* push = nullptr, HgeHalfSchedule* tile = nullptr,
              bool accumulate = false) {
   hge_incidence* inc = st->inc;
-  const HgeHalfSchedule& s = tile ? *tile
-                             : node_half ? inc->node_half
-                                         : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
+  HgeHalfSchedule& s = tile ? *tile
+                       : node_half ? inc->node_half
+                                   : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
+  if (st->ctx->kernel == 0) return run_half_stream(st, s, node_half, sweep, raw, push, accumulate);
   HalfSweepArgs a;
   a.idx = s.idx;
   a.yg = reinterpret_cast<const float4*>(node_half ? st->ye : st->yn);
@@ -1304,8 +1192,18 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
     hge_algdist_destroy(st);
     return code;
   };
-  if ((rc = hge_dev_alloc(ctx, &st->yn, (size_t)inc->N * st->ld)) != HGE_OK) return fail(rc);
-  if ((rc = hge_dev_alloc(ctx, &st->ye, (size_t)inc->E * st->ld)) != HGE_OK) return fail(rc);
+  // one block [edge rows | a row of zeros | node rows]: the packed gather stream addresses the
+  // gathered rows, a row's own old value and its padding as rows of the same allocation
+  if ((rc = hge_dev_alloc(ctx, &st->ybuf, ((size_t)inc->E + 1 + (size_t)inc->N) * st->ld)) != HGE_OK)
+    return fail(rc);
+  st->ye = st->ybuf;
+  st->yn = st->ybuf + ((size_t)inc->E + 1) * st->ld;
+  st->zero_row = (uint32_t)inc->E;
+  if (cudaMemsetAsync(st->ybuf + (size_t)inc->E * st->ld, 0, (size_t)st->ld * sizeof(float), ctx->stream) !=
+      cudaSuccess) {
+    hge_set_error("hge_algdist_create: memset failed");
+    return fail(HGE_ERR_CUDA);
+  }
   if ((rc = hge_dev_alloc(ctx, &st->mm, (size_t)std::max(1, max_iterations) * 2 * st->ld)) != HGE_OK)
     return fail(rc);
   // node rows far beyond what random gathers reach at full rate: tile the edge half (single
@@ -1349,6 +1247,7 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
     default: rc = occupancy_grid<32>(ctx, &st->grid); break;
   }
   if (rc != HGE_OK) return fail(rc);
+  if ((rc = hge_sweep_resident_blocks(st->lpr, &st->sweep_resident)) != HGE_OK) return fail(rc);
   *out = st;
   return HGE_OK;
 }
@@ -1357,8 +1256,7 @@ int hge_algdist_destroy(hge_algdist* st) {
   if (!st) return HGE_OK;
   cudaSetDevice(st->ctx->device);
   const hge_ctx* ctx = st->ctx;
-  hge_dev_free(ctx, st->yn);
-  if (st->owns_ye) hge_dev_free(ctx, st->ye);
+  hge_dev_free(ctx, st->ybuf);   // (a peer-memory arena owns the rows otherwise)
   hge_dev_free(ctx, st->mm);
   hge_dev_free(ctx, st->partials);
   hge_dev_free(ctx, st->tile_raw);

@@ -57,6 +57,32 @@ int hge_ctx_stage(hge_ctx* ctx, size_t floats, float** out) {
   return HGE_OK;
 }
 
+// Schedule / kernel defaults (hge_ctx_create, hge_ctx_reset_tuning); the environment variables
+// are read on every reset so a variant sweep can steer a whole process.
+static void set_default_tuning(hge_ctx* ctx) {
+  // schedule defaults from the sweep in profiles/r1_half_sweep_experiments.md (config 2, 4-block
+  // kernel): sub-warp rows up to degree 128, chunks of 1024, a grid of 4 x the resident blocks
+  ctx->light_max_deg = 128;
+  ctx->chunk = 1024;
+  ctx->blocks_per_sm = 0;  // 0: 4 x what the occupancy calculator says is resident
+  // half-sweep kernel: 0 = k_sweep over the packed gather stream (csrc/hge_sweep.cu), 1 = the
+  // first-generation k_half_sweep over the CSR work items (kept for A/B measurements)
+  ctx->kernel = 0;
+  if (const char* env = getenv("HGE_KERNEL")) ctx->kernel = strcmp(env, "items") == 0 ? 1 : 0;
+  // cost of a unit (a chunk of a long row, a group of short rows) in steps of 4 gathers, used to
+  // cut the stream into pieces of equal cost
+  ctx->unit_cost = 1;
+  if (const char* env = getenv("HGE_UNIT_COST")) ctx->unit_cost = atoi(env);
+  // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
+  // the edge half over more than 512 MB of node rows is tiled by node range into L2-sized tiles
+  // when the edges are large enough for that to pay (profiles/r1_tiled_edge_half.md)
+  ctx->tile_mb = 64;
+  ctx->tile_min_mb = 512;
+  if (const char* env = getenv("HGE_TILE_MB")) ctx->tile_mb = atoi(env);
+  if (const char* env = getenv("HGE_TILE_MIN_MB")) ctx->tile_min_mb = atoi(env);
+  ctx->tile_force = ctx->tile_min_mb == 0;
+}
+
 extern "C" {
 
 int hge_version(void) { return 100; }
@@ -88,22 +114,7 @@ int hge_ctx_create(int device, void* stream, hge_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->own_stream = false;
-  // schedule defaults from the sweep in profiles/r1_half_sweep_experiments.md (config 2, 4-block
-  // kernel): sub-warp rows up to degree 128, chunks of 1024, a grid of 4 x the resident blocks
-  ctx->light_max_deg = 128;
-  ctx->chunk = 1024;
-  ctx->blocks_per_sm = 0;  // 0: 4 x what the occupancy calculator says is resident
-  // measured slower than the register gather (profiles/r1_bulk_copy_experiment.md): opt-in
-  ctx->use_bulk = 0;
-  if (const char* env = getenv("HGE_BULK")) ctx->use_bulk = atoi(env) != 0;
-  // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
-  // the edge half over more than 512 MB of node rows is tiled by node range into L2-sized tiles
-  // when the edges are large enough for that to pay (profiles/r1_tiled_edge_half.md)
-  ctx->tile_mb = 64;
-  ctx->tile_min_mb = 512;
-  if (const char* env = getenv("HGE_TILE_MB")) ctx->tile_mb = atoi(env);
-  if (const char* env = getenv("HGE_TILE_MIN_MB")) ctx->tile_min_mb = atoi(env);
-  ctx->tile_force = ctx->tile_min_mb == 0;
+  set_default_tuning(ctx);
   ctx->launches = 0;
   ctx->pinned_ring = nullptr;
   ctx->pinned_next = 0;
@@ -186,9 +197,19 @@ int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb) {
   return HGE_OK;
 }
 
-int hge_ctx_set_bulk(hge_ctx* ctx, int enabled) {
-  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_bulk: ctx is NULL");
-  ctx->use_bulk = enabled != 0;
+int hge_ctx_set_kernel(hge_ctx* ctx, int kernel, int unit_cost) {
+  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_kernel: ctx is NULL");
+  HGE_REQUIRE(kernel == 0 || kernel == 1, "hge_ctx_set_kernel: kernel %d not in {0, 1}", kernel);
+  HGE_REQUIRE(unit_cost >= 0 && unit_cost <= 1024, "hge_ctx_set_kernel: unit_cost %d not in [0, 1024]",
+              unit_cost);
+  ctx->kernel = kernel;
+  if (unit_cost) ctx->unit_cost = unit_cost;
+  return HGE_OK;
+}
+
+int hge_ctx_reset_tuning(hge_ctx* ctx) {
+  HGE_REQUIRE(ctx != nullptr, "hge_ctx_reset_tuning: ctx is NULL");
+  set_default_tuning(ctx);
   return HGE_OK;
 }
 

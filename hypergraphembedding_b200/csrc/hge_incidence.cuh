@@ -30,6 +30,38 @@ struct HgeHeavyRow {    // 32 B
   int32_t pad;
 };
 
+// Packed gather stream of a half schedule, built for one group count G = 32 / (lanes per row)
+// by hge_sched_stream (csrc/hge_schedule.cu) and read by k_sweep (csrc/hge_sweep.cu).
+//
+// A "step" is 4 gathered rows for each of the G lane groups of a warp: 4 G row indices, stored
+// group-major ([g][4]) so a warp reads one contiguous block per step.  A "unit" is either one
+// chunk of a long row (the groups share the chunk's incidences) or one group of
+// G consecutive short rows of the degree-sorted order (group g gathers row g); its steps are
+// consecutive in the stream and the units themselves are laid out back to back, long-row
+// chunks first.  Row indices are absolute rows of the ONE allocation that holds the gathered
+// and the owned table (gather0 / own0 = first row of either, zero = a row of zeros used as
+// padding), so a slot costs one multiply-add and one load, with no predicate.  With with_own
+// the last slot of a short row's last step is the row itself: its old value arrives through
+// the same pipeline as the neighbours'.  `piece` cuts the unit list into `pieces` contiguous
+// runs of equal cost (steps + unit_cost per unit), one per warp of the grid.
+struct HgeStream {
+  int G = 0;
+  int with_own = 0;
+  uint32_t gather0 = 0, own0 = 0, zero = 0;
+  int pieces = 0;
+  int unit_cost = 0;
+  int32_t* ids = nullptr;        // [(total_steps + kStreamSlackSteps) * 4 G]
+  int4* items = nullptr;         // [n_quads * G + kStreamSlackItems]: {row (-1: none), degree, steps of the unit, 1 / weight sum}
+  uint32_t* uoff = nullptr;      // [n_units + 1] first step of every unit
+  int32_t* piece = nullptr;      // [pieces + 1] first unit of every piece
+  int32_t n_units = 0;
+  int32_t n_quads = 0;
+  uint32_t total_steps = 0;
+};
+constexpr int kStreamStepAlign = 4;     // k_sweep's unroll: the steps of a long-row chunk are padded to it
+constexpr int kStreamSlackSteps = 12;  // the id look-ahead of k_sweep reads past the last step
+constexpr int kStreamSlackItems = 128; // ... and its descriptor ring past the last descriptor
+
 struct HgeHalfSchedule {
   int32_t rows = 0;
   int64_t nnz = 0;
@@ -50,6 +82,7 @@ struct HgeHalfSchedule {
   int32_t chunk_sz = 0;
   int32_t max_deg = 0;
   int32_t first_empty = -1;       // first row without incidences, or -1
+  HgeStream stream;               // packed form of the work items for k_sweep (built on first use)
   // transient, between hge_sched_begin and hge_sched_finish (csrc/hge_schedule.cu)
   int32_t row0 = 0;
   int32_t* sorted_rows = nullptr; // device: row ids by descending degree
@@ -69,6 +102,9 @@ int hge_sched_begin_ranges(hge_ctx* ctx, int32_t row0, int32_t row1, const int64
                            const int64_t* row_end, int64_t max_degree_possible,
                            HgeHalfSchedule* s);
 int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s);
+// Builds (or keeps, when the parameters match) the packed gather stream of a finished schedule.
+int hge_sched_stream(hge_ctx* ctx, HgeHalfSchedule* s, int G, int with_own, uint32_t gather0,
+                     uint32_t own0, uint32_t zero, int pieces);
 void hge_sched_release(const hge_ctx* ctx, HgeHalfSchedule* s);
 
 struct hge_incidence {
@@ -102,9 +138,9 @@ struct hge_incidence {
 struct hge_p2p {
   hge_ctx* ctx = nullptr;
   int rank = 0, world = 1;
-  int32_t E = 0, ld = 0, own_rows = 0;      // own_rows = ceil(E / world)
+  int32_t E = 0, N = 0, ld = 0, own_rows = 0;   // own_rows = ceil(E / world); N = local node rows
   char* base = nullptr;                      // local arena
-  size_t off_ye = 0, off_stage = 0, off_mmx = 0, off_flags = 0, off_err = 0, bytes = 0;
+  size_t off_ye = 0, off_stage = 0, off_mmx = 0, off_flags = 0, off_err = 0, off_yn = 0, bytes = 0;
   char* peer_base[16] = {nullptr};           // peer arenas (own slot = base)
   // device-side pointer tables [world]
   float4** d_peer_stage = nullptr;
@@ -121,9 +157,12 @@ struct hge_algdist {
   hge_incidence* inc = nullptr;
   int R = 0, ld = 0, ld4 = 0, lpr = 0, slabs = 1;
   int max_iters = 0;
+  float* ybuf = nullptr;        // [E + 1 + N, ld]: edge rows, a row of zeros, node rows (nullptr: the
+                                // rows live in a peer-memory arena with the same order)
   float* yn = nullptr;
   float* ye = nullptr;
-  bool owns_ye = true;          // false: ye lives in a peer-memory arena
+  uint32_t zero_row = 0;        // row of zeros, counted from ye
+  int sweep_resident = 1;       // resident blocks per SM of k_sweep
   int32_t* mm = nullptr;        // [max_iters][2][ld]
   float* tile_raw = nullptr;    // [E, ld] un-normalised edge sums accumulated over the tiles
   float4* partials = nullptr;   // max over the two halves

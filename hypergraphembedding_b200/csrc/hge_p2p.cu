@@ -12,9 +12,12 @@
 //                                      peers, signals, waits, and reduces them locally
 //                                                                   -> all-reduce(min / max)
 //
-// Each rank owns one cudaMalloc arena [edge rows | staging | bounds | flags | error] that the
-// other ranks of the node map through CUDA IPC.  Barriers are sequence-numbered flags: rank r
-// writes seq into flags[r] of every peer (release, system scope) and spins on its own flags
+// Each rank owns one cudaMalloc arena [edge rows | row of zeros | staging | bounds | flags |
+// error | local node rows] that the other ranks of the node map through CUDA IPC (the node rows
+// are never touched by a peer; they live here so that the packed gather stream of k_sweep can
+// address gathered rows, own rows and padding as rows of one allocation).  Barriers are
+// sequence-numbered flags: rank r writes seq into flags[r] of every peer (release, system scope)
+// and spins on its own flags
 // (acquire, system scope) with a wall-clock timeout that raises an error flag instead of
 // hanging.  One process per GPU: the spinning kernels of different ranks run on different
 // devices.
@@ -188,9 +191,11 @@ int launch_exchange(hge_algdist* st, int sweep_for_mm) {
 
 extern "C" {
 
-int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_edges, int ld, hge_p2p** out) {
+int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, int32_t num_edges,
+                   int ld, hge_p2p** out) {
   HGE_REQUIRE(ctx && out, "hge_p2p_create: NULL argument");
   *out = nullptr;
+  HGE_REQUIRE(num_local_nodes >= 0, "hge_p2p_create: negative node count");
   HGE_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world,
               "hge_p2p_create: rank %d / world %d not supported (world <= 16)", rank, world);
   HGE_REQUIRE(num_edges > 0 && ld > 0 && ld % 4 == 0, "hge_p2p_create: bad shape");
@@ -201,11 +206,12 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_edges, int ld,
   p->rank = rank;
   p->world = world;
   p->E = num_edges;
+  p->N = num_local_nodes;
   p->ld = ld;
   p->own_rows = (num_edges + world - 1) / world;
   size_t off = 0;
   p->off_ye = off;
-  off = align_up(off + (size_t)num_edges * ld * 4, 256);
+  off = align_up(off + ((size_t)num_edges + 1) * ld * 4, 256);   // + the row of zeros
   p->off_stage = off;
   off = align_up(off + (size_t)world * p->own_rows * ld * 4, 256);
   p->off_mmx = off;
@@ -214,6 +220,10 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_edges, int ld,
   off = align_up(off + (size_t)world * kFlagStride * 4, 256);
   p->off_err = off;
   off = align_up(off + 256, 256);
+  // offsets above are the same on every rank (peers address them); the node rows differ in size
+  off = align_up(off, (size_t)ld * 4);
+  p->off_yn = off;
+  off = align_up(off + (size_t)num_local_nodes * ld * 4, 256);
   p->bytes = off;
   // IPC-exportable memory must come from cudaMalloc, not from the stream-ordered pool
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p->base), p->bytes);
@@ -317,11 +327,12 @@ int hge_algdist_attach_p2p(hge_algdist* st, hge_p2p* p) {
   HGE_REQUIRE(st && p, "hge_algdist_attach_p2p: NULL argument");
   HGE_REQUIRE(st->inc->sharded, "hge_algdist_attach_p2p: the incidence is not a shard");
   HGE_REQUIRE(p->peers_open, "hge_algdist_attach_p2p: hge_p2p_open_peers has not been called");
-  HGE_REQUIRE(p->E == st->inc->E && p->ld == st->ld && p->ctx == st->ctx,
+  HGE_REQUIRE(p->E == st->inc->E && p->N == st->inc->N && p->ld == st->ld && p->ctx == st->ctx,
               "hge_algdist_attach_p2p: arena shape does not match the relaxation state");
-  if (st->owns_ye) hge_dev_free(st->ctx, st->ye);
+  hge_dev_free(st->ctx, st->ybuf);
   st->ye = reinterpret_cast<float*>(p->base + p->off_ye);
-  st->owns_ye = false;
+  st->yn = reinterpret_cast<float*>(p->base + p->off_yn);
+  st->zero_row = (uint32_t)p->E;
   st->p2p = p;
   return HGE_OK;
 }

@@ -150,6 +150,124 @@ __global__ void k_sched_heavy_write(int32_t n_heavy, const int32_t* __restrict__
   }
 }
 
+// ---- packed gather stream (HgeStream) ---------------------------------------------------
+
+// steps[u] of every unit (chunks of long rows first, then groups of G short rows); steps[n_units] = 0
+__global__ void k_unit_steps(int32_t n_units, int32_t n_chunks, int64_t n_light, int G, int with_own,
+                             int chunk, const int2* __restrict__ chunks,
+                             const HgeHeavyRow* __restrict__ hrows,
+                             const HgeLightItem* __restrict__ light, uint32_t* __restrict__ steps) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u <= n_units;
+       u += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t st = 0;
+    if (u < n_chunks) {
+      const int2 ch = chunks[u];
+      const int cnt = min(chunk, hrows[ch.x].deg - ch.y * chunk);
+      st = (uint32_t)((cnt + 4 * G - 1) / (4 * G));
+      st = (st + kStreamStepAlign - 1) / kStreamStepAlign * kStreamStepAlign;
+    } else if (u < n_units) {
+      // rows are sorted by descending degree: the first row of the group is its longest
+      const int64_t first = (u - n_chunks) * G;
+      const int d = first < n_light ? (int)(light[first].deg_hi & 0xffu) : 0;
+      st = (uint32_t)max(1, (d + with_own + 3) / 4);
+    }
+    steps[u] = st;
+  }
+}
+
+// one block per chunk of a long row: its column ids in storage order, padded with the zero row
+__global__ void k_stream_heavy(int32_t n_chunks, int G, int chunk, uint32_t gather0, uint32_t zero,
+                               const int2* __restrict__ chunks, const HgeHeavyRow* __restrict__ hrows,
+                               const int32_t* __restrict__ idx, const uint32_t* __restrict__ uoff,
+                               int32_t* __restrict__ ids) {
+  for (int32_t u = blockIdx.x; u < n_chunks; u += gridDim.x) {
+    const int2 ch = chunks[u];
+    const HgeHeavyRow hr = hrows[ch.x];
+    const int cnt = min(chunk, hr.deg - ch.y * chunk);
+    const int32_t* src = idx + hr.start + (int64_t)ch.y * chunk;
+    const uint32_t pos = uoff[u];
+    const int total = (int)(uoff[u + 1] - pos) * 4 * G;
+    int32_t* dst = ids + (size_t)pos * 4 * G;
+    for (int j = threadIdx.x; j < total; j += blockDim.x)
+      dst[j] = j < cnt ? (int32_t)(gather0 + (uint32_t)src[j]) : (int32_t)zero;
+  }
+}
+
+// one warp per group of G short rows: slot (step s, group g, j) holds incidence 4 s + j of row g,
+// the zero row beyond the row's degree, and (with_own) the row itself in the group's last slot
+__global__ void k_stream_light(int32_t n_quads, int32_t n_chunks, int64_t n_light, int G, int with_own,
+                               uint32_t gather0, uint32_t own0, uint32_t zero,
+                               const HgeLightItem* __restrict__ light, const int32_t* __restrict__ idx,
+                               const uint32_t* __restrict__ uoff, int32_t* __restrict__ ids,
+                               int4* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t q = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); q < n_quads; q += warps) {
+    const uint32_t pos = uoff[n_chunks + q];
+    const int steps = (int)(uoff[n_chunks + q + 1] - pos);
+    if (lane < G) {
+      const int64_t i = q * G + lane;
+      int4 it = make_int4(-1, 0, steps, 0);
+      if (i < n_light) {
+        const HgeLightItem li = light[i];
+        it.x = li.row;
+        it.y = (int)(li.deg_hi & 0xffu);
+        it.w = __float_as_int(li.invs);
+      }
+      items[i] = it;
+    }
+    const int total = steps * 4 * G;
+    int32_t* dst = ids + (size_t)pos * 4 * G;
+    for (int f = lane; f < total; f += 32) {
+      const int g = (f >> 2) % G;
+      const int k = (f / (4 * G)) * 4 + (f & 3);
+      const int64_t i = q * G + g;
+      int32_t v = (int32_t)zero;
+      if (i < n_light) {
+        const HgeLightItem li = light[i];
+        const int d = (int)(li.deg_hi & 0xffu);
+        if (k < d) {
+          const int64_t start = ((int64_t)(li.deg_hi >> 8) << 32) | (int64_t)li.start_lo;
+          v = (int32_t)(gather0 + (uint32_t)idx[start + k]);
+        } else if (with_own && k == steps * 4 - 1) {
+          v = (int32_t)(own0 + (uint32_t)li.row);
+        }
+      }
+      dst[f] = v;
+    }
+  }
+}
+
+// what k_sweep reads past the end: zero-row ids for its id look-ahead, descriptors that never
+// finish for its descriptor ring
+__global__ void k_stream_slack(int n, uint32_t zero, int32_t* __restrict__ dst, int4* __restrict__ items) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    dst[i] = (int32_t)zero;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kStreamSlackItems; i += gridDim.x * blockDim.x)
+    items[i] = make_int4(-1, 0, 0x7fffffff, 0);
+}
+
+// piece[p] = first unit whose cost prefix (steps before it + unit_cost per unit before it)
+// reaches p / pieces of the total
+__global__ void k_piece_bounds(int pieces, int32_t n_units, int unit_cost,
+                               const uint32_t* __restrict__ uoff, int32_t* __restrict__ piece) {
+  const unsigned long long total = (unsigned long long)uoff[n_units] + (unsigned long long)unit_cost * n_units;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p <= pieces; p += gridDim.x * blockDim.x) {
+    if (p == pieces) {
+      piece[p] = n_units;
+      continue;
+    }
+    const unsigned long long want = total * (unsigned long long)p / (unsigned long long)pieces;
+    int32_t lo = 0, hi = n_units;
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      const unsigned long long c = (unsigned long long)uoff[mid] + (unsigned long long)unit_cost * mid;
+      if (c < want) lo = mid + 1; else hi = mid;
+    }
+    piece[p] = lo;
+  }
+}
+
 int grid_for(const hge_ctx* ctx, int64_t work, int per_block) {
   const int64_t want = std::max<int64_t>(1, (work + per_block - 1) / per_block);
   return (int)std::min<int64_t>(want, (int64_t)ctx->num_sms * 16);
@@ -275,7 +393,91 @@ int hge_sched_finish(hge_ctx* ctx, const char* what, HgeHalfSchedule* s) {
   return HGE_OK;
 }
 
+static void stream_release(const hge_ctx* ctx, HgeStream* t) {
+  hge_dev_free(ctx, t->ids);
+  hge_dev_free(ctx, t->items);
+  hge_dev_free(ctx, t->uoff);
+  hge_dev_free(ctx, t->piece);
+  *t = HgeStream();
+}
+
+int hge_sched_stream(hge_ctx* ctx, HgeHalfSchedule* s, int G, int with_own, uint32_t gather0,
+                     uint32_t own0, uint32_t zero, int pieces) {
+  HgeStream& t = s->stream;
+  const int unit_cost = ctx->unit_cost;
+  if (t.ids && t.G == G && t.with_own == with_own && t.gather0 == gather0 && t.own0 == own0 &&
+      t.zero == zero && t.pieces == pieces && t.unit_cost == unit_cost)
+    return HGE_OK;
+  stream_release(ctx, &t);
+  HGE_REQUIRE(G >= 1 && G <= 32 && pieces >= 1, "hge_sched_stream: bad group count / piece count");
+  const int64_t n_quads = (s->n_light + G - 1) / G;
+  const int64_t n_units = (int64_t)s->n_chunks + n_quads;
+  if (n_units >= INT32_MAX) {
+    hge_set_error("gather stream needs more than 2^31-1 units");
+    return HGE_ERR_UNSUPPORTED;
+  }
+  t.G = G;
+  t.with_own = with_own;
+  t.gather0 = gather0;
+  t.own0 = own0;
+  t.zero = zero;
+  t.pieces = pieces;
+  t.unit_cost = unit_cost;
+  t.n_units = (int32_t)n_units;
+  t.n_quads = (int32_t)n_quads;
+  uint32_t* steps = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &steps, (size_t)n_units + 1));
+  HGE_TRY(hge_dev_alloc(ctx, &t.uoff, (size_t)n_units + 1));
+  k_unit_steps<<<grid_for(ctx, n_units + 1, kBlock), kBlock, 0, ctx->stream>>>(
+      t.n_units, s->n_chunks, s->n_light, G, with_own, s->chunk_sz, s->chunks, s->hrows, s->light, steps);
+  HGE_CHECK_LAUNCH(ctx);
+  size_t temp_bytes = 0;
+  HGE_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, steps, t.uoff, n_units + 1, ctx->stream));
+  char* temp = nullptr;
+  HGE_TRY(hge_dev_alloc(ctx, &temp, temp_bytes));
+  HGE_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, steps, t.uoff, n_units + 1, ctx->stream));
+  ctx->launches += 1;
+  hge_dev_free(ctx, temp);
+  hge_dev_free(ctx, steps);
+  // the one host wait: the stream's length (a 32-bit sum that wrapped shows as a mismatch with
+  // the 64-bit bound below)
+  uint32_t* h_total = static_cast<uint32_t*>(hge_ctx_pinned_slot(ctx));
+  if (!h_total) return HGE_ERR_NOMEM;
+  HGE_CUDA(cudaMemcpyAsync(h_total, t.uoff + n_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  t.total_steps = *h_total;
+  const double bound = (double)s->nnz / 4.0 + 2.0 * (double)n_units + 64.0 * 256.0;
+  if (bound > 4.0e9) {
+    hge_set_error("gather stream of %.3g steps does not fit 32-bit step offsets", bound);
+    return HGE_ERR_UNSUPPORTED;
+  }
+  const size_t n_ids = ((size_t)t.total_steps + kStreamSlackSteps) * 4 * G;
+  HGE_TRY(hge_dev_alloc(ctx, &t.ids, n_ids));
+  HGE_TRY(hge_dev_alloc(ctx, &t.items, (size_t)n_quads * G + kStreamSlackItems));
+  HGE_TRY(hge_dev_alloc(ctx, &t.piece, (size_t)pieces + 1));
+  if (s->n_chunks) {
+    k_stream_heavy<<<(int)std::min<int64_t>(s->n_chunks, (int64_t)ctx->num_sms * 16), kBlock, 0, ctx->stream>>>(
+        s->n_chunks, G, s->chunk_sz, gather0, zero, s->chunks, s->hrows, s->idx, t.uoff, t.ids);
+    HGE_CHECK_LAUNCH(ctx);
+  }
+  if (n_quads) {
+    k_stream_light<<<grid_for(ctx, n_quads, kBlock / 32), kBlock, 0, ctx->stream>>>(
+        t.n_quads, s->n_chunks, s->n_light, G, with_own, gather0, own0, zero, s->light, s->idx, t.uoff,
+        t.ids, t.items);
+    HGE_CHECK_LAUNCH(ctx);
+  }
+  k_stream_slack<<<1, kBlock, 0, ctx->stream>>>(kStreamSlackSteps * 4 * G, zero,
+                                                t.ids + (size_t)t.total_steps * 4 * G,
+                                                t.items + (size_t)n_quads * G);
+  HGE_CHECK_LAUNCH(ctx);
+  k_piece_bounds<<<grid_for(ctx, pieces + 1, kBlock), kBlock, 0, ctx->stream>>>(pieces, t.n_units, unit_cost,
+                                                                              t.uoff, t.piece);
+  HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
+}
+
 void hge_sched_release(const hge_ctx* ctx, HgeHalfSchedule* s) {
+  stream_release(ctx, &s->stream);
   hge_dev_free(ctx, s->sorted_rows);
   hge_dev_free(ctx, s->d_stats);
   if (s->stats_ready) cudaEventDestroy(s->stats_ready);

@@ -110,6 +110,7 @@ class NativeOps(object):
                                    sharded=True, num_slices=num_slices)
     self.num_slices = num_slices
     self.num_edges = num_edges
+    self.num_local_nodes = n_loc
     self.state = None
 
   def edge_sums(self):
@@ -156,12 +157,13 @@ class NativeOps(object):
     shape is re-used; otherwise one is created, its 64-byte IPC handle swapped with the other
     ranks and the peers' arenas mapped."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    key = (id(self.ctx), id(group), rank, world, self.num_edges, self.ld)
+    key = (id(self.ctx), id(group), rank, world, self.num_local_nodes, self.num_edges, self.ld)
     entry = _ARENA_POOL.get(key) if pooled else None
     if entry is not None and not entry["in_use"]:
       self.arena = entry["arena"]
     else:
-      self.arena = _native.PeerArena(self.ctx, rank, world, self.num_edges, self.ld)
+      self.arena = _native.PeerArena(self.ctx, rank, world, self.num_local_nodes, self.num_edges,
+                                     self.ld)
       mine = self.torch.from_numpy(self.arena.export()).to(self.device)
       every = [self.torch.empty_like(mine) for _ in range(world)]
       dist.all_gather(every, mine, group=group)

@@ -62,11 +62,12 @@ int hge_ctx_sync(hge_ctx* ctx);
  *   chunk          incidences per warp work item for longer rows (default 1024)
  *   blocks_per_sm  grid size = SMs * blocks_per_sm (default: 4 x the resident blocks) */
 int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_per_sm);
-/* Experimental: gather the long rows (more than light_max_deg incidences) through the
- * bulk-copy engine (cp.async.bulk into a shared-memory ring, k_heavy_bulk) instead of the
- * register gather of k_half_sweep.  Same results; measured slower for 128-byte rows
- * (profiles/r1_bulk_copy_experiment.md), so it is off by default. */
-int hge_ctx_set_bulk(hge_ctx* ctx, int enabled);
+/* Half-sweep kernel selection (A/B measurements; results differ only by fp32 summation order):
+ *   kernel     0 = k_sweep, fed by a packed gather stream laid out in consumption order (default);
+ *              1 = the first-generation k_half_sweep over 16-byte CSR work items
+ *   unit_cost  cost of one unit of work in steps of 4 gathers when the stream is cut into
+ *              equal-cost pieces, one per warp (0 keeps the default of 1) */
+int hge_ctx_set_kernel(hge_ctx* ctx, int kernel, int unit_cost);
 /* Edge half over node rows that exceed what random 128-byte gathers reach at full rate
  * (measured on config 5: 1.9 TB/s over 8.3 GB of rows, 4.9 TB/s inside 1 GB, 6.3 TB/s inside an
  * L2-sized block): when the (local) node rows exceed min_rows_mb megabytes the half-sweep runs
@@ -79,6 +80,8 @@ int hge_ctx_set_bulk(hge_ctx* ctx, int enabled);
  * half on one GPU, 200 -> 159 ms per step on 8.  Results differ from the untiled half-sweep only
  * by fp32 summation order. */
 int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb);
+/* Back to the defaults of hge_ctx_create for every knob above (tuning, kernel, tiles). */
+int hge_ctx_reset_tuning(hge_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hge_ctx_launch_count(const hge_ctx* ctx);
 
@@ -164,7 +167,8 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
  * call the same sequence of sweeps; each rank must drive its own GPU.  A barrier that is not
  * met within 20 s raises an error flag (hge_p2p_check) instead of hanging. */
 typedef struct hge_p2p hge_p2p;
-int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_edges, int ld, hge_p2p** out);
+int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, int32_t num_edges,
+                   int ld, hge_p2p** out);
 int hge_p2p_export(hge_p2p* p, void* handle64);
 int hge_p2p_open_peers(hge_p2p* p, const void* handles /* world x 64 bytes */);
 int hge_p2p_check(hge_p2p* p);

@@ -135,7 +135,31 @@ def test_tuning_knobs_do_not_change_results(gpu_ctx):
       xn, xe = _run(A, xn0, xe0, 5, gpu_ctx)
       assert np.abs(xn - base[0]).max() < 2e-6 and np.abs(xe - base[1]).max() < 2e-6
   finally:
-    gpu_ctx.set_tuning(64, 512, 0)
+    gpu_ctx.reset_tuning()      # the library's own defaults, not a copy of them
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_both_half_sweep_kernels_against_the_oracle(kernel, gpu_ctx):
+  """The stream-fed k_sweep (default) and the first-generation k_half_sweep on a graph with
+  short rows, single-chunk and multi-chunk long rows, R not a multiple of 4."""
+  from oracle import port
+  rng = np.random.default_rng(17)
+  n, e = 9000, 400
+  rows = np.concatenate([np.arange(n), rng.integers(0, n, 50000), rng.integers(0, 300, 30000),
+                         rng.integers(0, n, e)])
+  cols = np.concatenate([np.zeros(n, int), rng.integers(0, e, 50000), rng.integers(0, e, 30000),
+                         np.arange(e)])
+  A = csr_from_pairs(np.stack([rows, cols], 1), shape=(n, e))
+  for R in (32, 10):
+    xn0 = rng.random((n, R)).astype(np.float32)
+    xe0 = rng.random((e, R)).astype(np.float32)
+    ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, 6)
+    try:
+      gpu_ctx.set_kernel(kernel)
+      xn, xe = _run(A, xn0, xe0, 6, gpu_ctx)
+    finally:
+      gpu_ctx.reset_tuning()
+    assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
 
 
 def test_results_are_reproducible_run_to_run(gpu_ctx):
@@ -201,6 +225,6 @@ def test_node_range_tiles_of_the_edge_half(gpu_ctx):
       results.append((xn, xe))
       assert np.abs(xn - want_n).max() < 2e-5 and np.abs(xe - want_e).max() < 2e-5, tile_mb
   finally:
-    gpu_ctx.set_tile_mb(64, 1024)
+    gpu_ctx.reset_tuning()
   assert np.array_equal(results[1][0], results[2][0]) and np.array_equal(results[1][1], results[2][1])
   assert np.abs(results[0][1] - results[1][1]).max() < 5e-6
