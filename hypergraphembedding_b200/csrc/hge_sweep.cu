@@ -32,6 +32,21 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef HGE_SWEEP_MIN_BLOCKS
 #define HGE_SWEEP_MIN_BLOCKS 4
 #endif
+// 1: the running per-column min / max of the rows a thread produced live in registers (8) instead
+// of shared memory (a 128-bit shared-memory access of a warp is 4 wavefronts of the L1 data pipe,
+// the busiest unit of the node half: 67 % in profiles/r2_half_sweep.md)
+#ifndef HGE_SWEEP_MINMAX_REGS
+#define HGE_SWEEP_MINMAX_REGS 1
+#endif
+// 1: the constants of the lazily applied affine map live in registers (8) as well
+#ifndef HGE_SWEEP_AFFINE_REGS
+#define HGE_SWEEP_AFFINE_REGS 0
+#endif
+// measurement-only builds (wrong results): 1 = finished rows are dropped, 2 = ids are not
+// broadcast inside the lane group, 4 = descriptors are not read
+#ifndef HGE_SWEEP_DEBUG
+#define HGE_SWEEP_DEBUG 0
+#endif
 #ifndef HGE_SWEEP_PREFETCH_STEPS
 #define HGE_SWEEP_PREFETCH_STEPS 24
 #endif
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
 
   // per-thread constants of the lazily applied affine map and the running min / max of the rows
   // this thread produced: shared memory instead of 16 registers (touched once per finished row)
-  __shared__ float4 s_state[kOwn ? 4 * kBlock : 1];
+  __shared__ float4 s_state[kOwn ? ((HGE_SWEEP_MINMAX_REGS ? 0 : 2) + (HGE_SWEEP_AFFINE_REGS ? 0 : 2)) * kBlock + 1 : 1];
   __shared__ float4 s_min[kOwn ? kWarps : 1][LPR];
   __shared__ float4 s_max[kOwn ? kWarps : 1][LPR];
   // row descriptors of the short rows, two halves of 32 per warp, filled by asynchronous copies
@@ -124,6 +139,7 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
   const char* const basel = reinterpret_cast<const char*>(a.base + c4c);
   const uint32_t row_bytes = (uint32_t)ld4 * 16u;
 
+  float4 rinv = make_float4(1.f, 1.f, 1.f, 1.f), rc3 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kOwn) {
     float lo[4] = {0.f, 0.f, 0.f, 0.f}, inv[4] = {1.f, 1.f, 1.f, 1.f};
     if (a.mm_prev && active) {
@@ -139,13 +155,20 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     // x' = c1 y + (c2 acc - c3):  c1 = inv deg / 2;  node half (the gathered rows carry the map
     // too): c2 = inv invs / 2, c3 = inv lo;  edge half: c2 = invs / 2, c3 = inv lo / 2
     const float h = MODE == kSweepNode ? 1.0f : 0.5f;
-    sst[0] = make_float4(inv[0], inv[1], inv[2], inv[3]);
-    sst[kBlock] = make_float4(h * (lo[0] * inv[0]), h * (lo[1] * inv[1]), h * (lo[2] * inv[2]),
-                              h * (lo[3] * inv[3]));
+    rinv = make_float4(inv[0], inv[1], inv[2], inv[3]);
+    rc3 = make_float4(h * (lo[0] * inv[0]), h * (lo[1] * inv[1]), h * (lo[2] * inv[2]), h * (lo[3] * inv[3]));
+#if !HGE_SWEEP_AFFINE_REGS
+    sst[0] = rinv;
+    sst[kBlock] = rc3;
+#endif
+#if !HGE_SWEEP_MINMAX_REGS
     const float inf = __int_as_float(0x7f800000);
     sst[2 * kBlock] = make_float4(inf, inf, inf, inf);
     sst[3 * kBlock] = make_float4(-inf, -inf, -inf, -inf);
+#endif
   }
+  const float kInf = __int_as_float(0x7f800000);
+  float4 rmin = make_float4(kInf, kInf, kInf, kInf), rmax = make_float4(-kInf, -kInf, -kInf, -kInf);
 
   // ---- feeding ----------------------------------------------------------------------------
   const int32_t* const sp = a.stream + g * 4 + (K == 1 ? (gl & 3) : gl);
@@ -154,7 +177,11 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     for (int k = 0; k < K; ++k) r[k] = __ldcs(sp + (size_t)step * (4 * G) + LPR * k);
   };
   auto issue_one = [&](quad& v, const int (&r)[K], const int j) {
+#if HGE_SWEEP_DEBUG & 2
+    const int c = (r[0] + j) & 0xffff;
+#else
     const int c = __shfl_sync(kFull, r[K == 1 ? 0 : j / LPR], K == 1 ? j : j % LPR, LPR);
+#endif
     v = ldg_quad(basel + (size_t)(uint32_t)c * row_bytes);
   };
   auto issue = [&](quad (&v)[4], const int (&r)[K]) {
@@ -171,6 +198,10 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
   // ---- finishing ----------------------------------------------------------------------------
   // called by the lanes that own (row, c4); acc is the full gathered sum of the row
   auto finish_row = [&](int row, float degf, float invs, const float4& yown, const float4& acc) {
+#if HGE_SWEEP_DEBUG & 1
+    if (acc.x == 123.456f && yown.x == 654.321f) a.own[0] = acc;
+    return;
+#endif
     const size_t off = (size_t)row * ld4 + c4;
     if (MODE == kSweepPush) {
       // fused reduce-scatter: the partial row goes straight into the owning GPU's staging block
@@ -185,7 +216,11 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     } else if (MODE == kSweepRaw) {
       a.raw[off] = acc;
     } else {
+#if HGE_SWEEP_AFFINE_REGS
+      const float4 inv = rinv, c3 = rc3;
+#else
       const float4 inv = sst[0], c3 = sst[kBlock];
+#endif
       const float hd = 0.5f * degf, hs = 0.5f * invs;
       float4 x;
       if (MODE == kSweepNode) {
@@ -202,6 +237,12 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
       const float w = __frcp_rn(degf);
       a.own[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
       // padding columns (>= R) stay 0 and are not published, so no per-column mask here
+#if HGE_SWEEP_MINMAX_REGS
+      rmin.x = fminf(rmin.x, x.x); rmax.x = fmaxf(rmax.x, x.x);
+      rmin.y = fminf(rmin.y, x.y); rmax.y = fmaxf(rmax.y, x.y);
+      rmin.z = fminf(rmin.z, x.z); rmax.z = fmaxf(rmax.z, x.z);
+      rmin.w = fminf(rmin.w, x.w); rmax.w = fmaxf(rmax.w, x.w);
+#else
       float4 lo4 = sst[2 * kBlock], hi4 = sst[3 * kBlock];
       lo4.x = fminf(lo4.x, x.x); hi4.x = fmaxf(hi4.x, x.x);
       lo4.y = fminf(lo4.y, x.y); hi4.y = fmaxf(hi4.y, x.y);
@@ -209,6 +250,7 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
       lo4.w = fminf(lo4.w, x.w); hi4.w = fmaxf(hi4.w, x.w);
       sst[2 * kBlock] = lo4;
       sst[3 * kBlock] = hi4;
+#endif
     }
   };
   auto reduce_groups = [&](float4& v) {
@@ -371,7 +413,11 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
 
   // ---- per-column min / max of the rows this block produced -------------------------------------
   if (kOwn) {
+#if HGE_SWEEP_MINMAX_REGS
+    float4 lo4 = rmin, hi4 = rmax;
+#else
     float4 lo4 = sst[2 * kBlock], hi4 = sst[3 * kBlock];
+#endif
 #pragma unroll
     for (int off = LPR; off < 32; off <<= 1) {
       lo4.x = fminf(lo4.x, __shfl_xor_sync(kFull, lo4.x, off));

@@ -146,6 +146,68 @@ def gen_weights(ref, name, hg, xn, xe, same_type):
   save("weights_" + name, **out)
 
 
+def gen_extra(ref, name, hg, xn, xe, seed, same_type_digest):
+  """The exported functions no other golden pins: WeightByAlgebraicSpan (hg2v_weighting.py:170-192,
+  draws its own 5-dimensional embedding from np.random), WeightByDistanceCluster (:106-134),
+  SameTypeDistanceSample (hg2v_sample.py:546-576) on pairs with and without a shared neighbour,
+  and -- as a digest, the matrix has 5.69 M stored entries on the youtube fixture --
+  WeightBySameTypeDistance (:34-64)."""
+  hc = compressed(ref, hg)
+  emb = arrays_to_emb(ref, xn, xe)
+  W, S, U = ref.hg2v_weighting, ref.hg2v_sample, ref.hypergraph_util
+  out = dict(pairs=incidence_pairs(hc), xn=xn, xe=xe, seed=seed)
+  for alpha in (0, 0.3):
+    np.random.seed(seed)
+    a, b = W.WeightByAlgebraicSpan(hc, alpha)
+    for tag, m in (("n2e", a), ("e2n", b)):
+      for k, v in csr_parts(m).items():
+        out["span_a%s_%s_%s" % (alpha, tag, k)] = v
+  out["span_rng_pos"] = np.random.get_state()[2]
+  dim = 3
+  wc, hc_t = W.WeightByDistanceCluster(hc, 0.3, emb, np.linalg.norm, dim)
+  out["cluster_dim"] = dim
+  out["cluster_w"] = np.asarray(wc.todense())
+  out["cluster_ht"] = np.asarray(hc_t.todense())
+  # same-type probabilities: all co-member pairs of a few rows plus pairs that share nothing
+  n2e, e2n = U.ToCsrMatrix(hc), U.ToEdgeCsrMatrix(hc)
+  rng = np.random.default_rng(seed)
+  for tag, m, src, dst, is_edge in (("nn", n2e, emb.node, emb.edge, False),
+                                    ("ee", e2n, emb.edge, emb.node, True)):
+    rows = m.shape[0]
+    ia = rng.integers(0, rows, 400)
+    ib = rng.integers(0, rows, 400)
+    co = (m @ m.T).tocoo()
+    pick = rng.choice(co.nnz, size=min(600, co.nnz), replace=False)
+    ia = np.concatenate([ia, co.row[pick]])
+    ib = np.concatenate([ib, co.col[pick]])
+    probs = []
+    for i, j in zip(ia.tolist(), ib.tolist()):
+      rec = S.SameTypeDistanceSample((i, j), idx2target=m, source_half_emb=src, target_half_emb=dst,
+                                     is_edge=is_edge)
+      probs.append(rec.edge_edge_prob if is_edge else rec.node_node_prob)
+      assert (rec.left_edge_idx, rec.right_edge_idx) == (i, j) if is_edge else \
+          (rec.left_node_idx, rec.right_node_idx) == (i, j)
+    out["st_%s_left" % tag] = ia.astype(np.int32)
+    out["st_%s_right" % tag] = ib.astype(np.int32)
+    out["st_%s_prob" % tag] = np.asarray(probs, np.float32)
+  if same_type_digest:
+    t = time.time()
+    n2n, e2e = W.WeightBySameTypeDistance(hc, 0.3, emb, np.linalg.norm, True)
+    out["wbstd_ref_seconds"] = time.time() - t
+    for tag, m in (("n2n", n2n), ("e2e", e2e)):
+      p = csr_parts(m)
+      out["wbstd_%s_shape" % tag] = p["shape"]
+      out["wbstd_%s_nnz" % tag] = m.nnz
+      out["wbstd_%s_pattern_sha" % tag] = hashlib.sha256(
+          p["indptr"].astype(np.int64).tobytes() + p["indices"].astype(np.int64).tobytes()).hexdigest()
+      out["wbstd_%s_stride" % tag] = 97
+      out["wbstd_%s_data_strided" % tag] = p["data"][::97].astype(np.float32)
+      out["wbstd_%s_data_sum" % tag] = float(p["data"].astype(np.float64).sum())
+      out["wbstd_%s_data_min" % tag] = float(p["data"].min())
+      out["wbstd_%s_data_max" % tag] = float(p["data"].max())
+  save("extra_" + name, **out)
+
+
 def gen_boolean(ref, name, hg, k, num_samples, neg, seed, full):
   hc = compressed(ref, hg)
   np.random.seed(seed)
@@ -262,6 +324,9 @@ def main():
     gen_weights(ref, "tiny", g["tiny"], *embs["tiny"], same_type=True)
     gen_weights(ref, "rand25", g["rand25"], *embs["rand25"], same_type=True)
     gen_weights(ref, "youtube", g["youtube"], *embs["youtube"], same_type=False)
+  if want("extra"):
+    gen_extra(ref, "rand25", g["rand25"], *embs["rand25"], seed=31, same_type_digest=False)
+    gen_extra(ref, "youtube", g["youtube"], *embs["youtube"], seed=32, same_type_digest=True)
   if want("boolean"):
     gen_boolean(ref, "tiny", g["tiny"], 2, 3, 2, 5, full=True)
     gen_boolean(ref, "rand25", g["rand25"], 4, 6, 3, 6, full=True)

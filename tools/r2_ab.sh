@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 A/B of the half-sweep kernels on config 2 (run on the GPU box):
+# Round-2 A/B of the half-sweep kernel variants on config 2 (run on the GPU box):
 #   bash tools/r2_ab.sh > gpurun_out/r2_ab.log 2>&1
 set -u
 cd "$(dirname "$0")/.."
@@ -12,15 +12,12 @@ run() { # name, env..., -- tuning args
   echo "== $name"
   env "${envs[@]}" timeout 600 python tools/time_variant.py c2 "$@" 2>&1 | tail -1
 }
-run stream X=1 --
-run items HGE_KERNEL=items --
 for f in $V/libhge_*.so; do
   [ -e "$f" ] || continue
   run "$(basename $f)" HGE_LIB_PATH=$f --
 done
-run stream_uc1 HGE_UNIT_COST=1 --
-run stream_uc6 HGE_UNIT_COST=6 --
-run stream_2waves X=1 -- 128 1024 8
-run stream_4waves X=1 -- 128 1024 16
-run stream_l64 X=1 -- 64 1024 0
-run stream_l255_c2048 X=1 -- 255 2048 0
+run mb3_regs_3waves HGE_LIB_PATH=$V/libhge_mb3_regs.so -- 128 1024 9
+run mb3_regs_1wave HGE_LIB_PATH=$V/libhge_mb3_regs.so -- 128 1024 3
+run mb4_smem_uc0 HGE_LIB_PATH=$V/libhge_mb4_smem.so HGE_UNIT_COST=0 --
+run mb4_smem_3waves HGE_LIB_PATH=$V/libhge_mb4_smem.so -- 128 1024 12
+run items HGE_KERNEL=items --

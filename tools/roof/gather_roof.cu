@@ -1,0 +1,82 @@
+// Roof of the access pattern the half-sweep is made of: random gathers of 128-byte rows (one
+// float4 per lane, 8 lanes per row, 4 rows per warp-wide load) from a table of a given size,
+// U loads in flight per lane, ids read coalesced from a pre-drawn array.  Prints GB/s of
+// gathered bytes per table size: the L2-resident and the DRAM-resident ceilings of the pattern.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/roof/gather_roof tools/roof/gather_roof.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+template <int U>
+__global__ void __launch_bounds__(256) k_gather(const float4* __restrict__ table, const uint32_t* __restrict__ ids,
+                                              long long per_warp, float4* out) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t* p = ids + warp * per_warp * 4 + g;     // 4 ids per warp-step, one per group
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = 0; i < per_warp; i += U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t c = __ldcs(p + (i + u) * 4);
+      v[u] = __ldg(table + (size_t)c * 8 + gl);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+  }
+  if (acc.x == 123.456f) out[0] = acc;
+}
+
+__global__ void k_fill_ids(uint32_t* ids, long long n, uint32_t rows, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;
+    x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29; x *= 0x94D049BB133111EBull; x ^= x >> 32;
+    ids[i] = (uint32_t)(x % rows);
+  }
+}
+
+template <int U>
+float run(const float4* table, const uint32_t* ids, long long per_warp, int blocks, float4* out) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  k_gather<U><<<blocks, 256>>>(table, ids, per_warp, out);
+  CK(cudaEventRecord(a));
+  for (int r = 0; r < 5; ++r) k_gather<U><<<blocks, 256>>>(table, ids, per_warp, out);
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  float ms; CK(cudaEventElapsedTime(&ms, a, b));
+  return ms / 5;
+}
+
+int main() {
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  const long long total_gathers = 16ll << 20;            // 16M rows = 2 GB gathered per launch
+  uint32_t* ids; CK(cudaMalloc(&ids, total_gathers * 4));
+  float4* out; CK(cudaMalloc(&out, 64));
+  const size_t sizes_mb[] = {8, 32, 48, 64, 80, 96, 128, 192, 256, 1024, 8192};
+  printf("sms %d; gathered GB/s (rows of 128 B) by table size, blocks per SM and loads in flight per lane\n", sms);
+  for (size_t mb : sizes_mb) {
+    const uint32_t rows = (uint32_t)((mb << 20) / 128);
+    float4* table; CK(cudaMalloc(&table, (size_t)rows * 128));
+    CK(cudaMemset(table, 0, (size_t)rows * 128));
+    k_fill_ids<<<sms * 8, 256>>>(ids, total_gathers, rows, mb * 7919);
+    CK(cudaDeviceSynchronize());
+    for (int bps : {4, 8}) {
+      const int blocks = sms * bps;
+      const long long per_warp = total_gathers / 4 / ((long long)blocks * 8) / 16 * 16;
+      const double bytes = (double)per_warp * 4 * blocks * 8 * 128;
+      const float t8 = run<8>(table, ids, per_warp, blocks, out);
+      const float t16 = run<16>(table, ids, per_warp, blocks, out);
+      printf("table %5zu MB  blocks/SM %d  U=8: %7.0f GB/s  U=16: %7.0f GB/s\n", mb, bps, bytes / t8 / 1e6,
+             bytes / t16 / 1e6);
+    }
+    CK(cudaFree(table));
+  }
+  return 0;
+}
