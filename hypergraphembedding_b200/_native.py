@@ -215,9 +215,26 @@ class Context(object):
     stream_ptr = c_vp(int(stream)) if stream else None
     check(self.lib.hge_ctx_create(self.device, stream_ptr, ctypes.byref(handle)), "hge_ctx_create")
     self.handle = handle
+    self._stream = int(stream) if stream else 0
 
   def set_stream(self, stream):
     check(self.lib.hge_ctx_set_stream(self.handle, c_vp(int(stream)) if stream else None))
+    self._stream = int(stream) if stream else 0
+
+  def bind_torch_stream(self):
+    """Queues this context's work on torch's CURRENT stream of the device (a no-op while that
+    is the stream already bound; switching drains the old one).  Callers that interleave torch
+    collectives or kernels with library calls (distributed.py) rely on stream order, which only
+    holds when both sides use the same stream -- e.g. inside ``with torch.cuda.stream(s):``."""
+    try:
+      import torch
+    except ImportError:
+      return
+    if not torch.cuda.is_initialized():
+      return
+    current = int(torch.cuda.current_stream(self.device).cuda_stream)
+    if current != getattr(self, "_stream", 0):
+      self.set_stream(current)
 
   def set_tuning(self, light_max_deg=0, chunk=0, blocks_per_sm=0):
     check(self.lib.hge_ctx_set_tuning(self.handle, light_max_deg, chunk, blocks_per_sm))
@@ -256,8 +273,8 @@ _default_ctx = {}
 
 
 def default_context(device=None):
-  """Process-wide context on the current torch device's current stream (or device 0 with a
-  private stream when torch has not initialised CUDA)."""
+  """Process-wide context of the current torch device, bound to torch's current stream of that
+  device at every call (the legacy default stream when torch has not initialised CUDA)."""
   stream = None
   if device is None:
     device = 0
@@ -272,6 +289,7 @@ def default_context(device=None):
   if ctx is None:
     ctx = Context(key, stream)
     _default_ctx[key] = ctx
+  ctx.bind_torch_stream()
   return ctx
 
 

@@ -36,7 +36,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // of shared memory (a 128-bit shared-memory access of a warp is 4 wavefronts of the L1 data pipe,
 // the busiest unit of the node half: 67 % in profiles/r2_half_sweep.md)
 #ifndef HGE_SWEEP_MINMAX_REGS
-#define HGE_SWEEP_MINMAX_REGS 1
+#define HGE_SWEEP_MINMAX_REGS 0     // measured: 64 registers do not hold them without spills
 #endif
 // 1: the constants of the lazily applied affine map live in registers (8) as well
 #ifndef HGE_SWEEP_AFFINE_REGS
@@ -46,6 +46,15 @@ constexpr unsigned kFull = 0xffffffffu;
 // broadcast inside the lane group, 4 = descriptors are not read
 #ifndef HGE_SWEEP_DEBUG
 #define HGE_SWEEP_DEBUG 0
+#endif
+// distance, in groups of rows, at which the rows a warp will update are requested into L2 (0: off)
+#ifndef HGE_SWEEP_PREFETCH_OWN
+#define HGE_SWEEP_PREFETCH_OWN 1
+#endif
+// 1: while a round's rows are in flight, L2 is asked for the rows of the NEXT round (their ids are
+// in registers a round ahead): the loads of a round then mostly wait for L2, not for DRAM
+#ifndef HGE_SWEEP_PREFETCH_ROWS
+#define HGE_SWEEP_PREFETCH_ROWS 0
 #endif
 #ifndef HGE_SWEEP_PREFETCH_STEPS
 #define HGE_SWEEP_PREFETCH_STEPS 24
@@ -188,6 +197,15 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
 #pragma unroll
     for (int j = 0; j < 4; ++j) issue_one(v[j], r, j);
   };
+  auto prefetch_rows = [&](const int (&r)[K]) {
+#if HGE_SWEEP_PREFETCH_ROWS
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = __shfl_sync(kFull, r[K == 1 ? 0 : j / LPR], K == 1 ? j : j % LPR, LPR);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(basel + (size_t)(uint32_t)c * row_bytes));
+    }
+#endif
+  };
   // the id stream is read once, front to back: one lane per warp asks L2 for the line a few
   // steps ahead, so the register ring above only has to cover an L2 hit
   auto prefetch_ids = [&](uint32_t step) {
@@ -289,6 +307,8 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
         quad va[4], vb[4];
         issue(va, r[d]);
         issue(vb, r[d + 1]);
+        prefetch_rows(r[(d + 2) % D]);
+        prefetch_rows(r[(d + 3) % D]);
         load_ids(pos + i + d + D, r[d]);
         load_ids(pos + i + d + 1 + D, r[d + 1]);
         if (d == 0) prefetch_ids(pos + i);
@@ -352,6 +372,18 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     for (int d = 0; d < D; ++d) load_ids(pos + d, r[d]);
     cp_async_wait<1>();
     __syncwarp();
+    // A row's own old value is the one load of a round that always comes from DRAM (every row is
+    // read once per launch), and a round lasts as long as its slowest load.  The descriptors sit
+    // in the ring ahead of their use, so each lane asks L2 for the row of one descriptor half a
+    // ring (16 / G .. 48 / G groups of rows) before it is gathered.
+    auto prefetch_own = [&](int half) {
+      if (kOwn && HGE_SWEEP_PREFETCH_OWN) {
+        const int row = ring[half][lane].x;
+        if (row >= 0)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.own + (size_t)row * ld4 + slab * LPR));
+      }
+    };
+    prefetch_own(0);
     pair4 acc = pair4_zero();
     int left = ring[0][slot].z;
     int groups = u1 - q0;                          // groups of rows left in this piece
@@ -372,6 +404,13 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
         ++blk_next;
         slot &= 63;
       }
+      if (kOwn && HGE_SWEEP_PREFETCH_OWN && G <= 16 && (slot & 31) == 16 + g) {
+        // half way through this half of the ring: the other half (requested when this one was
+        // entered) has landed by now -- ask L2 for the rows it describes
+        cp_async_wait<0>();
+        __syncwarp();
+        prefetch_own(((slot >> 5) & 1) ^ 1);
+      }
       left = --groups == 0 ? 0x7fffffff : ring[slot >> 5][slot & 31].z;
     };
     for (uint32_t i = 0; i < total; i += D) {
@@ -384,6 +423,8 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
         quad va[4], vb[4];
         issue(va, r[d]);
         issue(vb, r[d + 1]);
+        prefetch_rows(r[(d + 2) % D]);
+        prefetch_rows(r[(d + 3) % D]);
         load_ids(pos + i + d + D, r[d]);
         load_ids(pos + i + d + 1 + D, r[d + 1]);
         if (d == 0) prefetch_ids(pos + i);

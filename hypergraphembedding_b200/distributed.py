@@ -152,22 +152,25 @@ class NativeOps(object):
     self.state.store(sweeps_done, xn, xe)
 
   # ---- peer-memory exchange (csrc/hge_p2p.cu) ------------------------------------------
-  def enable_p2p(self, dist, group, pooled=True):
+  def enable_p2p(self, dist, group, pooled=True, agree=None):
     """Attaches this rank's exchange arena to the relaxation state.  A pooled arena of the same
     shape is re-used; otherwise one is created, its 64-byte IPC handle swapped with the other
-    ranks and the peers' arenas mapped."""
+    ranks and the peers' arenas mapped.  `agree(fn, what)` makes a rank-local failure of the
+    arena allocation collective (ShardedRelaxation._all_or_none)."""
+    agree = agree or (lambda fn, what: fn())
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     key = (id(self.ctx), id(group), rank, world, self.num_local_nodes, self.num_edges, self.ld)
     entry = _ARENA_POOL.get(key) if pooled else None
     if entry is not None and not entry["in_use"]:
       self.arena = entry["arena"]
     else:
-      self.arena = _native.PeerArena(self.ctx, rank, world, self.num_local_nodes, self.num_edges,
-                                     self.ld)
+      self.arena = agree(lambda: _native.PeerArena(self.ctx, rank, world, self.num_local_nodes,
+                                                   self.num_edges, self.ld), "allocating the exchange arena")
       mine = self.torch.from_numpy(self.arena.export()).to(self.device)
       every = [self.torch.empty_like(mine) for _ in range(world)]
       dist.all_gather(every, mine, group=group)
-      self.arena.open_peers(self.torch.stack(every).cpu().numpy())
+      handles = self.torch.stack(every).cpu().numpy()
+      agree(lambda: self.arena.open_peers(handles), "mapping the peers' exchange arenas")
       dist.barrier(group=group)
       entry = {"arena": self.arena, "ctx": self.ctx, "in_use": False}
       if pooled and key not in _ARENA_POOL:
@@ -220,16 +223,21 @@ class ShardedRelaxation(object):
     self.num_local_nodes, self.num_edges = ops_kwargs.get("shape") or A_local.shape
     num_slices = max(1, min(int(num_slices), self.num_edges))
     factory = ops_factory or NativeOps
-    self.ops = factory(A_local, self.R, self.iterations, num_slices, **ops_kwargs)
+    ctx = ops_kwargs.get("ctx")
+    if ctx is not None and hasattr(ctx, "bind_torch_stream"):
+      ctx.bind_torch_stream()     # the collectives below are ordered with the kernels by stream
+    self.ops = self._all_or_none(lambda: factory(A_local, self.R, self.iterations, num_slices, **ops_kwargs),
+                                 "uploading the shard")
     # the one set-up exchange: global edge degrees and the edges' weight sums
     deg, wsum = self.ops.edge_sums()
     w0 = dist.all_reduce(deg, op=dist.ReduceOp.SUM, group=group, async_op=True)
     w1 = dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=group, async_op=True)
     w0.wait()
     w1.wait()
-    if bool((deg == 0).any()):
+    if bool((deg == 0).any()):       # all-reduced: every rank sees it
       raise ZeroDivisionError("an edge has no incidence on any rank (algebraic_distance.py:49)")
-    self.ops.finish()
+    # an isolated NODE is only seen by the rank that holds it: agree before the next collective
+    self._all_or_none(self.ops.finish, "building the shard's schedule")
     self.num_slices = num_slices
     # exchange strategy: "p2p" = fused into the kernels over peer memory (one node, one GPU
     # per rank), "nccl" = host-interleaved NCCL / gloo collectives
@@ -240,10 +248,37 @@ class ShardedRelaxation(object):
       raise RuntimeError("peer-memory exchange needs NCCL ranks on distinct GPUs of one node")
     self.use_p2p = can_p2p and comm in ("auto", "p2p")
     if self.use_p2p:
-      self.ops.enable_p2p(dist, group)
+      self.ops.enable_p2p(dist, group, agree=self._all_or_none)
       self.partial = None
     else:
       self.partial = self.ops.new_partial_buffer()
+
+  def _all_or_none(self, fn, what):
+    """Runs a rank-local step that may fail (an isolated node, out of memory, a CUDA error) and
+    makes the outcome collective: the status word is all-reduced (MAX), and when any rank failed
+    EVERY rank raises before the next collective instead of waiting in it for the NCCL timeout.
+    A ZeroDivisionError (the reference's 0/0 on an isolated node, algebraic_distance.py:49) is
+    raised as such on all ranks."""
+    torch, dist = self.torch, self.dist
+    result, error, code = None, None, 0
+    try:
+      result = fn()
+    except ZeroDivisionError as exc:
+      error, code = exc, 1
+    except Exception as exc:       # noqa: BLE001 -- re-raised below, on every rank
+      error, code = exc, 2
+    status = torch.tensor([code], dtype=torch.int32)
+    if dist.get_backend(self.group) == "nccl":
+      status = status.cuda()
+    dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+    worst = int(status.item())
+    if error is not None:
+      raise error
+    if worst == 1:
+      raise ZeroDivisionError("a node on another rank has no incidence (algebraic_distance.py:49)")
+    if worst:
+      raise RuntimeError("another rank failed while %s; see its log" % what)
+    return result
 
   def _one_gpu_per_rank_on_one_node(self):
     import socket
@@ -289,9 +324,16 @@ class ShardedRelaxation(object):
     be identical on every rank)."""
     if self.iterations == 0:
       return xn_local, xe
+    ctx = getattr(self.ops, "ctx", None)
+    if ctx is not None and hasattr(ctx, "bind_torch_stream"):
+      ctx.bind_torch_stream()
     self.ops.load(xn_local, xe)
     for t in range(self.iterations):
       self.sweep(t)
+      if t == 0 and self.use_p2p and self.check_barriers:
+        # a rank that never arrives shows at the first barrier: stop here, not after
+        # `iterations` sweeps over rows that were never exchanged
+        self.ops.check_p2p()
     self.ops.store(self.iterations, xn_local, xe)
     if self.use_p2p and self.check_barriers:
       self.ops.check_p2p()

@@ -3,16 +3,16 @@
 ``EmbedHg2vNeighborhoodWeightedJaccard``:358, ``EmbedHg2vAlgDist``:387 (HOBE) and the matching
 entries of ``EMBEDDING_OPTIONS``:417 -- what ``runner.py --embedding-method HG2V_*`` calls.
 
-Same arguments, defaults, RNG consumption order (sampler first, then the model's initial
-tables, then one shuffle per epoch) and result (a ``HypergraphEmbedding`` keyed by the original
+Same arguments, defaults, consumption of the global numpy RNG (the sampler's draws, then one
+seed draw per embedding table as Keras' initializers make, then one shuffle per epoch) and result (a ``HypergraphEmbedding`` keyed by the original
 ids with the reference's ``method_name``).  Sampling and training run in libhge_b200.so.
 """
 import logging
 
 from .algebraic_distance import EmbedAlgebraicDistance
 from .hg2v_model import (BooleanModel, EarlyStopping, KerasModelToEmbedding, UnweightedFloatModel)
-from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, SamplesToModelInput,
-                          WeightedJaccardSamples)
+from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, PlotDistributions,
+                          SamplesToModelInput, WeightedJaccardSamples)
 from .hg2v_weighting import UniformWeight, WeightByNeighborhood
 from .hypergraph_util import CompressRange
 
@@ -30,9 +30,7 @@ def _hypergraph2vec_skeleton(hypergraph, dimension, num_neighbors, sampler_fn, m
   samples = sampler_fn(compressed_hg)
 
   if debug_summary_path is not None:
-    # PlotDistributions (hg2v_sample.py:800-826) needs matplotlib, which is not a dependency
-    log.warning("debug_summary_path=%r ignored: the distribution plots need matplotlib",
-                debug_summary_path)
+    PlotDistributions(debug_summary_path, samples)
 
   log.info("Converting samples to model input")
   input_features, output_probs = SamplesToModelInput(samples, num_neighbors=num_neighbors,

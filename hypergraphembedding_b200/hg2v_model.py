@@ -16,8 +16,11 @@ tested against that):
              epsilon 1e-7, accumulators from 0), batching, the per-epoch
              ``np.random.shuffle`` of the sample order from the global numpy RNG, the epoch
              ``loss`` and EarlyStopping(monitor="loss") on it, the trained padding row 0;
-  different  the initial tables: Keras draws RandomUniform(-0.05, 0.05) from TensorFlow's RNG,
-             here the same distribution is drawn from the global numpy RNG (nodes, then edges);
+             what the GLOBAL numpy stream is advanced by: Keras' backend seeds each
+             RandomUniform initializer with one ``np.random.randint(10e6)`` (one draw per Embedding
+             layer, node layer first), then one shuffle per epoch;
+  different  the initial VALUES: Keras feeds that seed to TensorFlow's generator, here it seeds a
+             private ``np.random.RandomState`` per table (same distribution U(-0.05, 0.05));
              sums of duplicated rows' gradients inside a batch are fp32 atomics (order varies).
 """
 import ctypes
@@ -84,8 +87,14 @@ class Hg2vModel(object):
     self.ctx = ctx or _native.default_context()
     # Embedding(input_dim=max + 2): index 0 pads absent inputs (hg2v_model.py:75-84);
     # keras 'uniform' initializer = RandomUniform(-0.05, 0.05)
-    node0 = np.random.uniform(-0.05, 0.05, (max_node_idx + 2, self.dimension)).astype(np.float32)
-    edge0 = np.random.uniform(-0.05, 0.05, (max_edge_idx + 2, self.dimension)).astype(np.float32)
+    # the global stream moves by one randint per layer, as under Keras (K.random_uniform with
+    # seed=None draws np.random.randint(10e6)); the tables come from private generators
+    node_seed = np.random.randint(10e6)
+    edge_seed = np.random.randint(10e6)
+    node0 = np.random.RandomState(node_seed).uniform(
+        -0.05, 0.05, (max_node_idx + 2, self.dimension)).astype(np.float32)
+    edge0 = np.random.RandomState(edge_seed).uniform(
+        -0.05, 0.05, (max_edge_idx + 2, self.dimension)).astype(np.float32)
     self.node_rows, self.edge_rows = node0.shape[0], edge0.shape[0]
     lib = self.ctx.lib
     handle = _native.c_vp()

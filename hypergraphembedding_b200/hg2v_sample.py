@@ -742,3 +742,55 @@ def SamplesToModelInput(similarity_records, num_neighbors, weighted=True):
     features += padded("neighbor_edge_weights", 0)
   targets = [scalar("node_node_prob", 0), scalar("edge_edge_prob", 0), scalar("node_edge_prob", 0)]
   return (features, targets)
+
+
+################################################################################
+# Debug summary                                                                #
+################################################################################
+
+
+def PlotDistributions(debug_summary_path, sim_records):
+  """hg2v_sample.py:805-853: histograms of the per-entity weights and of the three probability
+  kinds, written to `debug_summary_path`.  matplotlib is an optional dependency; without it this
+  raises (the reference would have failed at import), it never skips the file silently."""
+  try:
+    import matplotlib
+    matplotlib.use("Agg")
+    import matplotlib.pyplot as plt
+  except ImportError as exc:
+    raise ImportError("debug_summary_path needs matplotlib for PlotDistributions "
+                      "(hg2v_sample.py:805-853): %s" % exc)
+  log.info("Writing Debug Summary to %s", debug_summary_path)
+  node2features, edge2features = {}, {}
+  for r in sim_records:
+    if r.left_weight is not None:
+      if r.left_node_idx is not None and r.left_node_idx not in node2features:
+        node2features[r.left_node_idx] = r.left_weight
+      if r.left_edge_idx is not None and r.left_edge_idx not in edge2features:
+        edge2features[r.left_edge_idx] = r.left_weight
+    if r.right_weight is not None:
+      if r.right_node_idx is not None and r.right_node_idx not in node2features:
+        node2features[r.right_node_idx] = r.right_weight
+      if r.right_edge_idx is not None and r.right_edge_idx not in edge2features:
+        edge2features[r.right_edge_idx] = r.right_weight
+  nn_probs = [r.node_node_prob for r in sim_records if r.node_node_prob is not None]
+  ee_probs = [r.edge_edge_prob for r in sim_records if r.edge_edge_prob is not None]
+  ne_probs = [r.node_edge_prob for r in sim_records if r.node_edge_prob is not None]
+  fig, (node_spans, edge_spans, nn_ax, ee_ax, ne_ax) = plt.subplots(5, 1, figsize=(8.5, 11))
+  if node2features:
+    node_spans.set_title("Node Weights")
+    node_spans.hist(list(node2features.values()))
+    node_spans.set_yscale("log")
+  if edge2features:
+    edge_spans.set_title("Edge Weights")
+    edge_spans.hist(list(edge2features.values()))
+    edge_spans.set_yscale("log")
+  for ax, title, probs in ((nn_ax, "Node-Node Probability Distribution", nn_probs),
+                           (ee_ax, "Edge-Edge Probability Distribution", ee_probs),
+                           (ne_ax, "Node-Edge Probability Distribution", ne_probs)):
+    ax.set_title(title)
+    ax.hist(probs)
+    ax.set_yscale("log")
+  fig.tight_layout()
+  fig.savefig(debug_summary_path)
+  plt.close(fig)

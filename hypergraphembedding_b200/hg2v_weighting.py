@@ -194,8 +194,10 @@ def ComputeSpans(hypergraph, embedding=None, run_in_parallel=True, disable_pbar=
     edge_span = _native.row_span(ctx, inc, xn, xe, 1)
   finally:
     inc.close()
-  node2span = {idx: float(node_span[idx]) for idx in hypergraph.node}
-  edge2span = {idx: float(edge_span[idx]) for idx in hypergraph.edge}
+  # a key beyond the incidence matrix (an entity nothing refers to) has span 0, as in the
+  # reference's _compute_span (`idx < idx2neighbors.shape[0]`, hg2v_weighting.py:219)
+  node2span = {idx: float(node_span[idx]) if idx < len(node_span) else 0 for idx in hypergraph.node}
+  edge2span = {idx: float(edge_span[idx]) if idx < len(edge_span) else 0 for idx in hypergraph.edge}
   return node2span, edge2span
 
 

@@ -200,3 +200,33 @@ def pair_worker(rank, world, port, backend, seed, num_pairs, alpha, out_dir, use
     np.savez(os.path.join(out_dir, "pairs%d.npz" % rank), w=np.asarray(w), lo=lo, hi=hi)
   finally:
     dist.destroy_process_group()
+
+
+def failure_worker(rank, world, port, backend, graph_args, out_dir):
+  """A node without incidences on the LAST rank only: every rank must raise (the same
+  ZeroDivisionError the reference raises) instead of one raising and the others waiting in the
+  next collective."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  import datetime
+  import torch.distributed as dist
+  from hypergraphembedding_b200 import distributed as hd
+  dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                          timeout=datetime.timedelta(seconds=60))
+  outcome = "no error"
+  try:
+    A = make_graph(*graph_args).tolil()
+    A[A.shape[0] - 3, :] = 0                      # lives in the last rank's block
+    A = sps.csr_matrix(A)
+    A.eliminate_zeros()
+    A_loc, r0, r1 = hd.local_shard(A, rank, world)
+    try:
+      hd.ShardedRelaxation(A_loc, 4, 2, ops_factory=NumpyOps)
+    except ZeroDivisionError as exc:
+      outcome = "ZeroDivisionError: %s" % exc
+    except Exception as exc:      # noqa: BLE001
+      outcome = "%s: %s" % (type(exc).__name__, exc)
+    with open(os.path.join(out_dir, "outcome%d.txt" % rank), "w") as f:
+      f.write(outcome)
+  finally:
+    dist.destroy_process_group()

@@ -75,3 +75,15 @@ def test_sharded_pair_weights_share_one_min_max(tmp_path):
   assert len(got) == len(done) == num_pairs // 2 and len(parts[1]["w"]) == 0
   assert np.abs(got - want).max() < 1e-5
   assert got.min() >= alpha - 1e-6 and abs(got.max() - 1.0) < 1e-6
+
+
+def test_rank_local_failure_is_raised_on_every_rank(tmp_path):
+  """An isolated node is only visible to the rank that holds it (the edge check is all-reduced,
+  the node check is not): the status word agreed after the local set-up makes both ranks raise
+  the reference's ZeroDivisionError (algebraic_distance.py:49) -- nobody is left in a collective."""
+  world = 2
+  mp.spawn(dist_helpers.failure_worker, args=(world, _free_port(), "gloo", (3, 400, 30, 2500), str(tmp_path)),
+           nprocs=world, join=True)
+  outcomes = [(tmp_path / ("outcome%d.txt" % r)).read_text() for r in range(world)]
+  assert all(o.startswith("ZeroDivisionError") for o in outcomes), outcomes
+  assert "another rank" in outcomes[0] and "another rank" not in outcomes[1]

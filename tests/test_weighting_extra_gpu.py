@@ -71,7 +71,8 @@ def test_weight_by_distance_cluster(name, monkeypatch):
 
 @pytest.mark.parametrize("name", ["rand25", "youtube"])
 def test_same_type_distance_sample_matches_reference(name):
-  from hypergraphembedding_b200 import SameTypeDistanceSample, ToCsrMatrix, ToEdgeCsrMatrix
+  from hypergraphembedding_b200 import ToCsrMatrix, ToEdgeCsrMatrix
+  from hypergraphembedding_b200.hg2v_sample import SameTypeDistanceSample
   g = load_golden("extra_" + name)
   hg = hypergraph_from_pairs(g["pairs"])
   emb = _embedding(g["xn"], g["xe"])

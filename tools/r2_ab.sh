@@ -12,12 +12,9 @@ run() { # name, env..., -- tuning args
   echo "== $name"
   env "${envs[@]}" timeout 600 python tools/time_variant.py c2 "$@" 2>&1 | tail -1
 }
+run default X=1 --
 for f in $V/libhge_*.so; do
   [ -e "$f" ] || continue
   run "$(basename $f)" HGE_LIB_PATH=$f --
 done
-run mb3_regs_3waves HGE_LIB_PATH=$V/libhge_mb3_regs.so -- 128 1024 9
-run mb3_regs_1wave HGE_LIB_PATH=$V/libhge_mb3_regs.so -- 128 1024 3
-run mb4_smem_uc0 HGE_LIB_PATH=$V/libhge_mb4_smem.so HGE_UNIT_COST=0 --
-run mb4_smem_3waves HGE_LIB_PATH=$V/libhge_mb4_smem.so -- 128 1024 12
 run items HGE_KERNEL=items --
