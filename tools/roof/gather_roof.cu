@@ -32,6 +32,72 @@ __global__ void __launch_bounds__(256) k_gather(const float4* __restrict__ table
   if (acc.x == 123.456f) out[0] = acc;
 }
 
+// The traffic mix of a half-sweep without any of its bookkeeping: every lane group owns one row
+// per round -- 8 gathers from the table, one 128-byte read and one 128-byte write of the owned
+// row.  own_random = 0: owned rows are visited in address order, 1: in a random order (what a
+// degree-sorted schedule does to them).
+__global__ void __launch_bounds__(256, 4) k_mix(const float4* __restrict__ table, const uint32_t* __restrict__ ids,
+                                               float4* own, const uint32_t* __restrict__ own_order,
+                                               long long rows_per_warp, int own_random) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t* p = ids + warp * rows_per_warp * 8 * 4 + g;
+  for (long long i = 0; i < rows_per_warp; ++i) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t c = __ldcs(p + (i * 8 + u) * 4);
+      v[u] = __ldg(table + (size_t)c * 8 + gl);
+    }
+    const long long r = (warp * rows_per_warp + i) * 4 + g;
+    const size_t orow = own_random ? own_order[r] : (size_t)r;
+    float4 acc = __ldcs(own + orow * 8 + gl);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+    own[orow * 8 + gl] = acc;
+  }
+}
+
+// The same mix with L2 eviction priorities: table rows evict_last, owned rows (read once,
+// written once) evict_first.
+__device__ __forceinline__ float4 ld_hint(const float4* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__global__ void __launch_bounds__(256, 4) k_mix_hint(const float4* __restrict__ table,
+                                                    const uint32_t* __restrict__ ids, float4* own,
+                                                    long long rows_per_warp, int own_first) {
+  unsigned long long keep, once;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(once));
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t* p = ids + warp * rows_per_warp * 8 * 4 + g;
+  for (long long i = 0; i < rows_per_warp; ++i) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t c = __ldcs(p + (i * 8 + u) * 4);
+      v[u] = ld_hint(table + (size_t)c * 8 + gl, keep);
+    }
+    const size_t orow = (size_t)((warp * rows_per_warp + i) * 4 + g);
+    float4 acc = own_first ? ld_hint(own + orow * 8 + gl, once) : __ldcs(own + orow * 8 + gl);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+    if (own_first)
+      asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(own + orow * 8 + gl),
+                   "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w), "l"(once) : "memory");
+    else
+      own[orow * 8 + gl] = acc;
+  }
+}
+
 __global__ void k_fill_ids(uint32_t* ids, long long n, uint32_t rows, uint64_t seed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint64_t x = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;
@@ -77,6 +143,62 @@ int main() {
              bytes / t16 / 1e6);
     }
     CK(cudaFree(table));
+  }
+  // ---- the mix of a half-sweep -------------------------------------------------------------
+  printf("\nmix: per owned row 8 gathers from the table + read and write of the row itself (128 B each);\n"
+         "GB/s counts gathered bytes only, ms is for 1M owned rows / 8M gathers (the node half of config 2\n"
+         "has 1M rows and 10M gathers from a 64 MB table, the edge half 500K rows and 10M gathers from 128 MB)\n");
+  {
+    const long long own_rows = 1ll << 20;                 // 128 MB of owned rows
+    float4* own; CK(cudaMalloc(&own, own_rows * 128));
+    CK(cudaMemset(own, 0, own_rows * 128));
+    uint32_t* order; CK(cudaMalloc(&order, own_rows * 4));
+    // a random permutation-like order (collisions do not matter for traffic)
+    k_fill_ids<<<sms * 8, 256>>>(order, own_rows, (uint32_t)own_rows, 12345);
+    for (size_t mb : {(size_t)64, (size_t)128}) {
+      const uint32_t rows = (uint32_t)((mb << 20) / 128);
+      float4* table; CK(cudaMalloc(&table, (size_t)rows * 128));
+      CK(cudaMemset(table, 0, (size_t)rows * 128));
+      k_fill_ids<<<sms * 8, 256>>>(ids, own_rows * 8, rows, mb * 104729);
+      CK(cudaDeviceSynchronize());
+      for (int bps : {4, 8}) {
+        const int blocks = sms * bps;
+        const long long rpw = own_rows / 4 / ((long long)blocks * 8);
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          cudaEvent_t a, b;
+          CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+          k_mix<<<blocks, 256>>>(table, ids, own, order, rpw, rnd);
+          CK(cudaEventRecord(a));
+          for (int r = 0; r < 5; ++r) k_mix<<<blocks, 256>>>(table, ids, own, order, rpw, rnd);
+          CK(cudaEventRecord(b));
+          CK(cudaEventSynchronize(b));
+          float ms; CK(cudaEventElapsedTime(&ms, a, b));
+          ms /= 5;
+          const double done_rows = (double)rpw * 4 * blocks * 8;
+          printf("table %4zu MB  blocks/SM %d  owned rows %s: %.4f ms  (%.0f GB/s gathered, %.0f GB/s with the owned rows)\n",
+                 mb, bps, rnd ? "random    " : "sequential", ms * (double)own_rows / done_rows,
+                 done_rows * 8 * 128 / ms / 1e6, done_rows * 10 * 128 / ms / 1e6);
+        }
+      }
+      for (int own_first = 0; own_first < 2; ++own_first) {
+        const int blocks = sms * 4;
+        const long long rpw = own_rows / 4 / ((long long)blocks * 8);
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        k_mix_hint<<<blocks, 256>>>(table, ids, own, rpw, own_first);
+        CK(cudaEventRecord(a));
+        for (int r = 0; r < 5; ++r) k_mix_hint<<<blocks, 256>>>(table, ids, own, rpw, own_first);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        ms /= 5;
+        const double done_rows = (double)rpw * 4 * blocks * 8;
+        printf("table %4zu MB  blocks/SM 4  table rows evict_last, owned rows %s: %.4f ms  (%.0f GB/s gathered)\n",
+               mb, own_first ? "evict_first" : "default    ", ms * (double)own_rows / done_rows,
+               done_rows * 8 * 128 / ms / 1e6);
+      }
+      CK(cudaFree(table));
+    }
   }
   return 0;
 }
