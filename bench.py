@@ -613,15 +613,14 @@ def run_ours(args, spec):
   # ---- end-to-end arm: host buffers through the C ABI --------------------------------------
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
   h_aptr, h_aidx = pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32))
-  h_bptr, h_bidx = pin(B.indptr.astype(np.int64)), pin(B.indices.astype(np.int32))
   h_xn0, h_xe0 = pin(xn0), pin(xe0)
   h_xn, h_xe = pin(np.empty_like(xn0)), pin(np.empty_like(xe0))
 
   def step_host():
     # the vectors are relaxed in place; the next step starts from this step's output, which is
     # again a valid input in [0, 1] (no host-to-host reset copy inside the timed region)
-    inc_h = _native.Incidence(ctx, N, E, h_aptr.numpy(), h_aidx.numpy(), h_bptr.numpy(),
-                              h_bidx.numpy())
+    # one orientation is uploaded; the library transposes it on the device
+    inc_h = _native.Incidence(ctx, N, E, h_aptr.numpy(), h_aidx.numpy())
     _native.algdist_run(ctx, inc_h, h_xn.numpy(), h_xe.numpy(), sweeps)
     inc_h.close()
 
@@ -639,8 +638,7 @@ def run_ours(args, spec):
     step_host()
   torch.cuda.synchronize()
   e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-  h2d = (h_aptr.numel() + h_bptr.numel()) * 8 + (h_aidx.numel() + h_bidx.numel()) * 4 + \
-      (h_xn0.numel() + h_xe0.numel()) * 4
+  h2d = h_aptr.numel() * 8 + h_aidx.numel() * 4 + (h_xn0.numel() + h_xe0.numel()) * 4
   d2h = (h_xn.numel() + h_xe.numel()) * 4
 
 
@@ -958,6 +956,49 @@ def run_community(args, spec, world, rank, local_rank):
     dist.destroy_process_group()
 
 
+def host_link_probe(world, rank, mb=256, reps=3):
+  """What the host side of the box gives N ranks at once: every rank copies `mb` MB of pinned
+  memory to its GPU and back, first rank 0 alone, then all ranks together (CUDA events, max over
+  ranks).  The end-to-end arm moves ~0.5 GB per rank and step through these links; when the
+  aggregate does not grow with N the host-buffer step cannot scale, whatever the kernels do."""
+  import torch
+  import torch.distributed as dist
+  n = mb << 18
+  host = torch.empty(n, dtype=torch.float32).pin_memory()
+  dev = torch.empty(n, dtype=torch.float32, device="cuda")
+
+  def timed(h2d):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+      if h2d:
+        dev.copy_(host, non_blocking=True)
+      else:
+        host.copy_(dev, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / reps
+
+  out = {}
+  for name, h2d in (("h2d", True), ("d2h", False)):
+    timed(h2d)                                   # warm-up
+    dist.barrier()
+    alone = torch.tensor([timed(h2d) if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
+    dist.barrier()
+    dist.all_reduce(alone, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    together = torch.tensor([timed(h2d)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(together, op=dist.ReduceOp.MAX)
+    gb = mb * (1 << 20) / 1e9
+    out[name + "_GBps_one_rank_alone"] = gb / (float(alone.item()) * 1e-3)
+    out[name + "_GBps_per_rank_all_ranks_at_once"] = gb / (float(together.item()) * 1e-3)
+    out[name + "_GBps_aggregate"] = world * gb / (float(together.item()) * 1e-3)
+  out["note"] = "%d MB pinned copies, CUDA events, slowest rank" % mb
+  del host, dev
+  return out
+
+
 def sharded_parity_check(world, rank, ctx, comm, slices, R=32, iters=10):
   """The multi-rank relaxation against the oracle before anything is timed: a 80 000-node /
   3 000-edge / ~0.98M-incidence hypergraph (the case of tests/check_multi_gpu_parity.py), node
@@ -1087,13 +1128,13 @@ def run_sharded(args, spec, world, rank, local_rank):
     bytes_launch = nnz_local * (4 * R + 4) + 2 * n_loc * 4 * R
     launch_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 1]) for t in range(sweeps)]))
   achieved = bytes_launch / (launch_ms * 1e-3) / 1e9
+  relax.close()      # its exchange arena goes back to the pool: the host-buffer steps re-use it
 
   # end to end: host buffers in, host buffers out, incidence upload and set-up collectives inside
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
   h_xn0, h_xe0 = pin(xn0), pin(xe0)
   h_xn, h_xe = pin(np.empty_like(xn0)), pin(np.empty_like(xe0))
-  h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32)),
-           pin(B.indptr.astype(np.int64)), pin(B.indices.astype(np.int32))]
+  h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32))]   # one orientation
 
   def step_host():
     r = hd.ShardedRelaxation(None, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
@@ -1117,10 +1158,9 @@ def run_sharded(args, spec, world, rank, local_rank):
                      device="cuda")
   dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
   e2e_ms = float(e2e.item())
-  h2d = (A.indptr.size + B.indptr.size) * 8 + (A.indices.size + B.indices.size) * 4 + \
-      (xn0.size + xe0.size) * 4 + E * 8
+  h2d = A.indptr.size * 8 + A.indices.size * 4 + (xn0.size + xe0.size) * 4
   d2h = (xn0.size + xe0.size) * 4
-  relax.close()
+  host_link = host_link_probe(world, rank)
   hd.release_peer_arenas(dist)
   del xn, xe, xn_init, xe_init
   torch.cuda.empty_cache()
@@ -1155,7 +1195,9 @@ def run_sharded(args, spec, world, rank, local_rank):
         "cpu_baseline": None,
         "e2e": {"value": nnz_global * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
                 "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * world,
-                "d2h_bytes_per_step": int(d2h) * world},
+                "d2h_bytes_per_step": int(d2h) * world, "host_link_GBps": host_link,
+                "copy_floor_ms": 1e3 * (h2d / (host_link["h2d_GBps_per_rank_all_ranks_at_once"] * 1e9) +
+                                        d2h / (host_link["d2h_GBps_per_rank_all_ranks_at_once"] * 1e9))},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "parity": parity,

@@ -306,17 +306,21 @@ class Incidence(object):
   `sharded=True` it is one shard of a node-partitioned hypergraph: all-reduce the arrays
   returned by `edge_sums()` over the shards, then call `finish_sharded()`."""
 
-  def __init__(self, ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx,
+  def __init__(self, ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr=None, e2n_idx=None,
                sharded=False, num_slices=1):
+    """e2n_ptr / e2n_idx None: the library builds the edge -> node orientation on the device."""
     self.ctx = ctx
     self.num_nodes = int(num_nodes)
     self.num_edges = int(num_edges)
     device = is_device(n2e_idx)
+    assert (e2n_ptr is None) == (e2n_idx is None)
     if device:
       keep = (n2e_ptr, n2e_idx, e2n_ptr, e2n_idx)   # borrowed by the library
       import torch
-      assert n2e_ptr.dtype == torch.int64 and e2n_ptr.dtype == torch.int64
-      assert n2e_idx.dtype == torch.int32 and e2n_idx.dtype == torch.int32
+      assert n2e_ptr.dtype == torch.int64 and n2e_idx.dtype == torch.int32
+      assert e2n_ptr is None or (e2n_ptr.dtype == torch.int64 and e2n_idx.dtype == torch.int32)
+    elif e2n_ptr is None:
+      keep = (_as_i64(n2e_ptr), _as_i32(n2e_idx), None, None)
     else:
       keep = (_as_i64(n2e_ptr), _as_i32(n2e_idx), _as_i64(e2n_ptr), _as_i32(e2n_idx))
     self._keep = keep
@@ -334,7 +338,7 @@ class Incidence(object):
             "hge_incidence_create_sharded")
     self.handle = handle
     self.nnz_n2e = int(keep[1].shape[0])
-    self.nnz_e2n = int(keep[3].shape[0])
+    self.nnz_e2n = int(keep[3].shape[0]) if keep[3] is not None else self.nnz_n2e
     if not device:
       self._keep = None  # the library copied the arrays
 

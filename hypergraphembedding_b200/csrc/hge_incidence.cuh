@@ -111,6 +111,7 @@ struct hge_incidence {
   hge_ctx* ctx = nullptr;
   int32_t N = 0, E = 0;
   bool owns_csr = false;
+  bool owns_e2n = false;           // borrowed node -> edge arrays, edge -> node built by the library
   int64_t* n2e_ptr = nullptr;
   int32_t* n2e_idx = nullptr;
   int64_t* e2n_ptr = nullptr;

@@ -59,11 +59,15 @@ _TOPOLOGY_OK = {}
 
 
 def release_peer_arenas(dist=None, group=None):
-  """Collective: unmaps and frees every pooled exchange arena.  Call on all ranks before the
-  process group is destroyed (otherwise the memory is released at process exit)."""
-  entries = [e for e in _ARENA_POOL.values() if not e["in_use"]]
-  for key in [k for k, e in _ARENA_POOL.items() if not e["in_use"]]:
-    del _ARENA_POOL[key]
+  """Collective: unmaps and frees every pooled exchange arena that is not attached to a live
+  relaxation.  Call on all ranks before the process group is destroyed (otherwise the memory is
+  released at process exit)."""
+  entries = []
+  for key in list(_ARENA_POOL):
+    entries += [e for e in _ARENA_POOL[key] if not e["in_use"]]
+    _ARENA_POOL[key] = [e for e in _ARENA_POOL[key] if e["in_use"]]
+    if not _ARENA_POOL[key]:
+      del _ARENA_POOL[key]
   if not entries:
     return
   if dist is None:
@@ -160,8 +164,11 @@ class NativeOps(object):
     agree = agree or (lambda fn, what: fn())
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     key = (id(self.ctx), id(group), rank, world, self.num_local_nodes, self.num_edges, self.ld)
-    entry = _ARENA_POOL.get(key) if pooled else None
-    if entry is not None and not entry["in_use"]:
+    # several relaxations of one shape can be alive at once (all ranks create and close them in
+    # the same order, so they pick the same pooled arena or miss together)
+    free = [e for e in _ARENA_POOL.get(key, []) if not e["in_use"]] if pooled else []
+    entry = free[0] if free else None
+    if entry is not None:
       self.arena = entry["arena"]
     else:
       self.arena = agree(lambda: _native.PeerArena(self.ctx, rank, world, self.num_local_nodes,
@@ -173,11 +180,11 @@ class NativeOps(object):
       agree(lambda: self.arena.open_peers(handles), "mapping the peers' exchange arenas")
       dist.barrier(group=group)
       entry = {"arena": self.arena, "ctx": self.ctx, "in_use": False}
-      if pooled and key not in _ARENA_POOL:
-        _ARENA_POOL[key] = entry
+      if pooled:
+        _ARENA_POOL.setdefault(key, []).append(entry)
     entry["in_use"] = True
     self._arena_entry = entry
-    self._arena_pooled = _ARENA_POOL.get(key) is entry
+    self._arena_pooled = pooled
     self.state.attach_p2p(self.arena)
     self._dist, self._group = dist, group
 

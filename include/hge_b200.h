@@ -92,7 +92,10 @@ int64_t hge_ctx_launch_count(const hge_ctx* ctx);
  * and unique inside a row, as scipy's canonical CSR is.  Builds the degree-binned gather
  * schedule and the inverse neighbour-weight sums used by the relaxation.
  * Rows without incidences are accepted here (the weighting entry points work on sparse id
- * ranges); the relaxation refuses them with HGE_ERR_EMPTY_ROW (hge_algdist_create / _run). */
+ * ranges); the relaxation refuses them with HGE_ERR_EMPTY_ROW (hge_algdist_create / _run).
+ * e2n_ptr == e2n_idx == NULL: the edge -> node orientation is built on the device from the
+ * node -> edge one (a stable radix sort of the (edge, node) pairs), so a host-buffer caller
+ * uploads one orientation only. */
 int hge_incidence_create(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                          const int64_t* n2e_ptr, const int32_t* n2e_idx,
                          const int64_t* e2n_ptr, const int32_t* e2n_idx, int mem,

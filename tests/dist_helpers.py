@@ -142,7 +142,7 @@ def worker(rank, world, port, backend, graph_args, R, iters, slices, out_dir, us
         # a second relaxation of the same shape re-uses the pooled exchange arena
         relax.close()
         relax = hd.ShardedRelaxation(A_loc, R, iters, num_slices=slices, comm=comm)
-        assert len(hd._ARENA_POOL) == 1
+        assert len(hd._ARENA_POOL) == 1 and len(list(hd._ARENA_POOL.values())[0]) == 1
         xn2 = torch.from_numpy(xn0[r0:r1].copy()).cuda()
         xe2 = torch.from_numpy(xe0.copy()).cuda()
         relax.run(xn2, xe2)

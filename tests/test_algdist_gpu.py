@@ -228,3 +228,34 @@ def test_node_range_tiles_of_the_edge_half(gpu_ctx):
     gpu_ctx.reset_tuning()
   assert np.array_equal(results[1][0], results[2][0]) and np.array_equal(results[1][1], results[2][1])
   assert np.abs(results[0][1] - results[1][1]).max() < 5e-6
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_edge_to_node_orientation_built_on_the_device(device, gpu_ctx):
+  """hge_incidence_create with e2n == NULL: the transpose the library builds (stable radix sort of
+  the (edge, node) pairs) gives the bits the caller-supplied orientation gives."""
+  import torch
+  from hypergraphembedding_b200 import _native
+  rng = np.random.default_rng(23)
+  A = _random_graph(rng, 4000, 300, 30000)
+  B = A.T.tocsr()
+  B.sort_indices()
+  xn0 = rng.random((4000, 32)).astype(np.float32)
+  xe0 = rng.random((300, 32)).astype(np.float32)
+  results = []
+  for with_e2n in (True, False):
+    arrays = [A.indptr.astype(np.int64), A.indices.astype(np.int32)]
+    if with_e2n:
+      arrays += [B.indptr.astype(np.int64), B.indices.astype(np.int32)]
+    if device:
+      arrays = [torch.from_numpy(a).cuda() for a in arrays]
+    inc = _native.Incidence(gpu_ctx, 4000, 300, *arrays)
+    xn = torch.from_numpy(xn0).cuda() if device else xn0.copy()
+    xe = torch.from_numpy(xe0).cuda() if device else xe0.copy()
+    _native.algdist_run(gpu_ctx, inc, xn, xe, 4)
+    # the weighting kernels walk the edge -> node arrays directly
+    d = _native.incidence_l2(gpu_ctx, inc, xn, xe, order=1)
+    inc.close()
+    results.append([np.asarray(t.cpu() if device else t) for t in (xn, xe, d)])
+  for a, b in zip(*results):
+    assert np.array_equal(a, b)

@@ -28,8 +28,7 @@ def main():
   xe0 = synthetic.legacy_initial_vectors(1, A.shape[1], R, seed=10**6)[1]
   pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
   h_xn, h_xe = pin(xn0), pin(xe0)
-  h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32)),
-           pin(B.indptr.astype(np.int64)), pin(B.indices.astype(np.int32))]
+  h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32))]   # one orientation
   marks = []
 
   def mark(name):
@@ -63,10 +62,35 @@ def main():
     mark("store (D2H)")
     ops.close()
     mark("close")
-    if rank == 0 and rep >= 2:
-      print("rep %d: " % rep + ", ".join("%s %.2f ms" % (n, (t - marks[i][1]) * 1e3)
-                                          for i, (n, t) in enumerate(marks[1:])) +
-            " | total %.2f ms" % ((marks[-1][1] - marks[0][1]) * 1e3), flush=True)
+    if rep >= 2:
+      line = "rank %d rep %d: " % (rank, rep) + ", ".join(
+          "%s %.2f ms" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + \
+          " | total %.2f ms" % ((marks[-1][1] - marks[0][1]) * 1e3)
+      lines = [None] * world
+      dist.all_gather_object(lines, line)
+      if rank == 0:
+        print("\n".join(lines), flush=True)
+  # the public path (ShardedRelaxation: the same steps plus the status agreements)
+  for rep in range(3):
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = hd.ShardedRelaxation(None, R, sweeps, ctx=ctx, shape=A.shape, csr_host=[t.numpy() for t in h_csr])
+    t1 = time.perf_counter()
+    r.run(h_xn.numpy(), h_xe.numpy())
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    r.close()
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    if rank == 0:
+      print("ShardedRelaxation rep %d: construct %.2f ms, run %.2f ms, close %.2f ms" %
+            (rep, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), flush=True)
+  from bench import host_link_probe
+  probe = host_link_probe(world, rank)
+  if rank == 0:
+    import json
+    print("host link: " + json.dumps(probe), flush=True)
   hd.release_peer_arenas(dist)
   dist.destroy_process_group()
 
