@@ -1120,11 +1120,11 @@ def run_sharded(args, spec, world, rank, local_rank):
   sweep_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 2]) for t in range(sweeps)]))
   peak, peak_src = hbm_peak()
   if relax.use_p2p:
-    kernel = "fused sweep: k_half_sweep<8> node half + edge gather with peer push + k_edge_reduce_push + 2 flag barriers (rank 0)"
+    kernel = "fused sweep: k_sweep<8> node half + sliced edge gather with peer push, per-slice barrier + k_edge_reduce_push on a second stream, min/max barrier (rank 0)"
     bytes_launch = algorithmic_bytes_per_sweep(n_loc, E, nnz_local, R)
     launch_ms = sweep_ms
   else:
-    kernel = "k_half_sweep<8> (node half, rank 0)"
+    kernel = "k_sweep<8, node> (rank 0)"
     bytes_launch = nnz_local * (4 * R + 4) + 2 * n_loc * 4 * R
     launch_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 1]) for t in range(sweeps)]))
   achieved = bytes_launch / (launch_ms * 1e-3) / 1e9

@@ -51,7 +51,6 @@ SIGNATURES = {
     "hge_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "hge_ctx_sync": (ctypes.c_int, [c_vp]),
     "hge_ctx_set_tuning": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
-    "hge_ctx_set_kernel": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hge_ctx_reset_tuning": (ctypes.c_int, [c_vp]),
     "hge_ctx_set_tile_mb": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "hge_ctx_launch_count": (ctypes.c_int64, [c_vp]),
@@ -81,7 +80,7 @@ SIGNATURES = {
     "hge_algdist_ld": (ctypes.c_int, [c_vp]),
     "hge_algdist_store": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_int]),
     "hge_p2p_create": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
-                                      ctypes.c_int, ctypes.POINTER(c_vp)]),
+                                      ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "hge_p2p_export": (ctypes.c_int, [c_vp, c_vp]),
     "hge_p2p_open_peers": (ctypes.c_int, [c_vp, c_vp]),
     "hge_p2p_check": (ctypes.c_int, [c_vp]),
@@ -245,10 +244,6 @@ class Context(object):
   def reset_tuning(self):
     """Every schedule / kernel / tile knob back to the library's defaults."""
     check(self.lib.hge_ctx_reset_tuning(self.handle))
-
-  def set_kernel(self, kernel, unit_cost=0):
-    """kernel 0: stream-fed k_sweep (default); 1: first-generation k_half_sweep."""
-    check(self.lib.hge_ctx_set_kernel(self.handle, int(kernel), int(unit_cost)))
 
   def sync(self):
     check(self.lib.hge_ctx_sync(self.handle), "hge_ctx_sync")
@@ -687,10 +682,11 @@ def sample_neighbors(n2e, e2n, nodes, edges, k, state):
 class PeerArena(object):
   """hge_p2p: the IPC-shared exchange arena of one shard."""
 
-  def __init__(self, ctx, rank, world, num_local_nodes, num_edges, ld):
+  def __init__(self, ctx, rank, world, num_local_nodes, num_edges, ld, slices=0):
+    """slices: pipelining depth of the exchange (0 = the library's default, 1 = not pipelined)."""
     self.ctx = ctx
     handle = c_vp()
-    check(ctx.lib.hge_p2p_create(ctx.handle, rank, world, num_local_nodes, num_edges, ld,
+    check(ctx.lib.hge_p2p_create(ctx.handle, rank, world, num_local_nodes, num_edges, ld, int(slices),
                                  ctypes.byref(handle)), "hge_p2p_create")
     self.handle = handle
     self.world = world

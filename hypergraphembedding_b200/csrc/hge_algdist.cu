@@ -183,17 +183,20 @@ __global__ void k_count_tile_pairs(int64_t total, int32_t rows, const int64_t* _
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
-// Reduce-scatter of locally accumulated partial rows: row r goes to the staging block of its
-// owner (rank r / own_rows), slot `rank` (the push the gather kernel does itself when untiled).
-__global__ void k_push_rows(int32_t rows, int ld4, const float4* __restrict__ raw,
-                            float4* const* __restrict__ peer_stage, int32_t own_rows, int rank) {
+// Reduce-scatter of locally accumulated partial rows [row0, row0 + rows): a row goes to the
+// staging block of its owner, slot `rank` (the push the gather kernel does itself when untiled).
+__global__ void k_push_rows(int32_t row0, int32_t rows, int ld4, const float4* __restrict__ raw,
+                            float4* const* __restrict__ peer_stage, int32_t own_rows, int rank,
+                            HgeOwnerMap map) {
   const int64_t total = (int64_t)rows * ld4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t r = (int32_t)(i / ld4);
-    const int c4 = (int)(i - (int64_t)r * ld4);
-    const int owner = r / own_rows;
-    peer_stage[owner][((size_t)rank * own_rows + (r - owner * own_rows)) * ld4 + c4] = __ldcs(raw + i);
+    const int32_t r = row0 + (int32_t)(i / ld4);
+    const int c4 = (int)(i - (int64_t)(r - row0) * ld4);
+    int owner;
+    int32_t idx;
+    map.locate(r, owner, idx);
+    peer_stage[owner][((size_t)rank * own_rows + idx) * ld4 + c4] = __ldcs(raw + (size_t)r * ld4 + c4);
   }
 }
 
@@ -257,454 +260,6 @@ __global__ void k_store_rows(int64_t rows, int R, int ld, const float* __restric
     }
     x[i] = v;
   }
-}
-
-// ----------------------------------------------------------------------------------------
-// the half-sweep kernel
-// ----------------------------------------------------------------------------------------
-
-struct HalfSweepArgs {
-  const int32_t* idx;          // CSR column ids of this half
-  const float4* yg;            // rows that are gathered        [*, ld4]
-  float4* yo;                  // rows that are owned / updated [rows, ld4]
-  const HgeLightItem* light;
-  int64_t n_light;
-  const HgeHeavyRow* hrows;
-  const int2* chunks;
-  int32_t n_chunks;
-  int32_t n_hrows;
-  int32_t chunk_sz;
-  float4* partials;            // [n_partials, ld4]
-  int32_t* counters;           // [slabs, n_hrows]
-  const int32_t* mm_prev;      // affine of the previous sweep, or nullptr (identity)
-  int32_t* mm_cur;             // min / max slots of this sweep
-  int32_t gather_affine;       // 1: gathered rows carry the previous sweep's affine (node half)
-  int32_t raw_out;             // 1: write the raw gathered sums to raw[rows, ld4] (sharded edge half);
-                               // 3: add them to raw (later node-range tiles of the edge half)
-  float4* raw;
-  // raw_out == 2: peer-memory push.  Row r belongs to rank r / push_rows; its raw sums go to
-  // that rank's staging block  push_stage[owner] + (push_rank * push_rows + r % push_rows) rows
-  float4* const* push_stage;
-  int32_t push_rows;
-  int32_t push_rank;
-  int32_t R;
-  int32_t ld4;
-};
-
-struct Affine {
-  float4 inv;     // 1 / (hi - lo)
-  float4 invlo;   // lo / (hi - lo)
-};
-
-// x' = (x_own + b) / 2 with x_own = inv (y deg) - inv lo and b = inv (acc invs) - inv lo (node
-// half) or b = acc invs (edge half), folded into two FMAs per component:
-//     x' = c1 y + (c2 acc + c3),  c1 = inv deg / 2,  c2 = inv invs / 2 | invs / 2,
-//     c3 = -inv lo | -inv lo / 2.   (the halvings are exact)
-__device__ __forceinline__ float4 finalize_value(const float4& yown, const float4& acc,
-                                                 float degf, float invs, const Affine& af,
-                                                 bool gather_affine) {
-  const float hd = 0.5f * degf, hs = 0.5f * invs;
-  float4 x;
-  if (gather_affine) {
-    x.x = fmaf(af.inv.x * hd, yown.x, fmaf(af.inv.x * hs, acc.x, -af.invlo.x));
-    x.y = fmaf(af.inv.y * hd, yown.y, fmaf(af.inv.y * hs, acc.y, -af.invlo.y));
-    x.z = fmaf(af.inv.z * hd, yown.z, fmaf(af.inv.z * hs, acc.z, -af.invlo.z));
-    x.w = fmaf(af.inv.w * hd, yown.w, fmaf(af.inv.w * hs, acc.w, -af.invlo.w));
-  } else {
-    x.x = fmaf(af.inv.x * hd, yown.x, fmaf(hs, acc.x, -0.5f * af.invlo.x));
-    x.y = fmaf(af.inv.y * hd, yown.y, fmaf(hs, acc.y, -0.5f * af.invlo.y));
-    x.z = fmaf(af.inv.z * hd, yown.z, fmaf(hs, acc.z, -0.5f * af.invlo.z));
-    x.w = fmaf(af.inv.w * hd, yown.w, fmaf(hs, acc.w, -0.5f * af.invlo.w));
-  }
-  return x;
-}
-
-// Compensated (Kahan) accumulation: a row can have 10^5..10^6 incidences and the relaxation
-// renormalises every sweep, so plain fp32 running sums are the dominant error term against the
-// reference's f64 arithmetic (measured on the youtube fixture: 2e-5 vs 1e-6 absolute).
-__device__ __forceinline__ void kahan_add(float4& s, float4& c, const float4& v) {
-  float y, t;
-  y = v.x - c.x; t = s.x + y; c.x = (t - s.x) - y; s.x = t;
-  y = v.y - c.y; t = s.y + y; c.y = (t - s.y) - y; s.y = t;
-  y = v.z - c.z; t = s.z + y; c.z = (t - s.z) - y; s.z = t;
-  y = v.w - c.w; t = s.w + y; c.w = (t - s.w) - y; s.w = t;
-}
-__device__ __forceinline__ float4 kahan_result(const float4& s, const float4& c) {
-  return make_float4(s.x - c.x, s.y - c.y, s.z - c.z, s.w - c.w);
-}
-
-// Adds n gathered rows to a compensated accumulator.  HGE_ACCUM_MODE selects how:
-//   0  plain running sum per lane (default).  A lane never adds more than chunk / G values in a
-//      row before the per-lane sums are combined pairwise across the sub-warps and the chunk
-//      sums are combined with compensation, so the blocked sum is already as accurate as the
-//      compensated ones: on the youtube fixture (an edge of 2 217 members) all three modes
-//      land at 1.0-1.1e-6 absolute distance error against the f64 reference
-//      (profiles/r1_variant_sweep.md).
-//   1  pairwise tree over the n values, then one compensated add of the block sum
-//   2  one compensated add per value
-#ifndef HGE_ACCUM_MODE
-#define HGE_ACCUM_MODE 0
-#endif
-template <int N>
-__device__ __forceinline__ void accumulate(float4& s, float4& c, float4 (&v)[N]) {
-#if HGE_ACCUM_MODE == 0
-#pragma unroll
-  for (int t = 0; t < N; ++t) hge_f4_add(s, v[t]);
-#elif HGE_ACCUM_MODE == 2
-#pragma unroll
-  for (int t = 0; t < N; ++t) kahan_add(s, c, v[t]);
-#else
-#pragma unroll
-  for (int stride = 1; stride < N; stride <<= 1) {
-#pragma unroll
-    for (int t = 0; t + stride < N; t += 2 * stride) hge_f4_add(v[t], v[t + stride]);
-  }
-  kahan_add(s, c, v[0]);
-#endif
-}
-
-// Resident blocks per SM and where the per-thread state of a row owner lives.  Measured on config 2
-// (profiles/r1_half_sweep_experiments.md): the kernel waits on memory ~65 % of every warp's time,
-// so what counts is warps per SM.  With the affine-map constants and the running min / max in
-// shared memory (16 registers) the kernel fits 64 registers with 44 bytes of spills: 4 blocks
-// = 32 warps per SM instead of 24, 0.454 -> 0.369 ms per sweep.
-#ifndef HGE_SMEM_STATE
-#define HGE_SMEM_STATE 1
-#endif
-#ifndef HGE_MIN_BLOCKS
-#define HGE_MIN_BLOCKS 4
-#endif
-
-// Per-thread state shared by the two gather kernels: which float4 column of which sub-warp this
-// lane is, the lazily applied affine map of the previous sweep, the running per-column min /
-// max, and what to do with a finished row.
-template <int LPR>
-struct RowOwner {
-  static constexpr int G = 32 / LPR;
-  const HalfSweepArgs& a;
-  int lane, gl, g, warp, slab, c4, ld4;
-  bool active, gaff, raw_out, m0, m1, m2, m3;
-#if HGE_SMEM_STATE
-  // the per-thread constants of the affine map and the running min / max live in shared memory
-  // (read / updated once per finished row): 16 registers less, a fourth resident block per SM
-  float4* sst;   // [4][threads]: inv, invlo, vmin, vmax of this thread
-  int sstride;
-#define HGE_AF_INV sst[0]
-#define HGE_AF_INVLO sst[sstride]
-#define HGE_VMIN sst[2 * sstride]
-#define HGE_VMAX sst[3 * sstride]
-#else
-  Affine af;
-  float4 vmin, vmax;
-#define HGE_AF_INV af.inv
-#define HGE_AF_INVLO af.invlo
-#define HGE_VMIN vmin
-#define HGE_VMAX vmax
-#endif
-
-  __device__ __forceinline__ explicit RowOwner(const HalfSweepArgs& args, float4* smem_state = nullptr,
-                                               int smem_stride = 0)
-      : a(args) {
-#if HGE_SMEM_STATE
-    sst = smem_state + threadIdx.x;
-    sstride = smem_stride;
-#endif
-    lane = threadIdx.x & 31;
-    gl = lane & (LPR - 1);
-    g = lane / LPR;
-    warp = threadIdx.x >> 5;
-    slab = blockIdx.y;                      // column slab of 32 float4 (R > 128 only)
-    c4 = slab * LPR + gl;                   // this lane's float4 column
-    ld4 = a.ld4;
-    active = c4 < ld4;
-    const int col0 = c4 * 4;
-    m0 = col0 + 0 < a.R;
-    m1 = col0 + 1 < a.R;
-    m2 = col0 + 2 < a.R;
-    m3 = col0 + 3 < a.R;
-    HGE_AF_INV = make_float4(1.f, 1.f, 1.f, 1.f);
-    HGE_AF_INVLO = hge_f4_zero();
-    if (a.mm_prev && active) {
-      float lo[4], inv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        lo[j] = 0.f;
-        inv[j] = 1.f;
-        if (col0 + j < a.R) {
-          lo[j] = hge_dec(a.mm_prev[col0 + j]);
-          const float hi = hge_dec(a.mm_prev[ld4 * 4 + col0 + j]);
-          inv[j] = 1.0f / (hi - lo[j]);
-        }
-      }
-      HGE_AF_INV = make_float4(inv[0], inv[1], inv[2], inv[3]);
-      HGE_AF_INVLO = make_float4(lo[0] * inv[0], lo[1] * inv[1], lo[2] * inv[2], lo[3] * inv[3]);
-    }
-    gaff = a.gather_affine != 0;
-    raw_out = a.raw_out != 0;
-    const float inf = __int_as_float(0x7f800000);
-    HGE_VMIN = make_float4(inf, inf, inf, inf);
-    HGE_VMAX = make_float4(-inf, -inf, -inf, -inf);
-  }
-
-  // called by the lanes that own (row, c4); acc is the full gathered sum
-  __device__ __forceinline__ void finish_row(int row, float degf, float invs, const float4& yown,
-                                             const float4& acc) {
-    const size_t off = (size_t)row * ld4 + c4;
-    if (raw_out) {
-      if (a.raw_out == 2) {
-        // fused reduce-scatter: the partial row is stored straight into the owning GPU's
-        // staging block over NVLink (one 128-byte line per sub-warp, posted write)
-        const int owner = row / a.push_rows;
-        float4* dst = a.push_stage[owner] +
-                      ((size_t)a.push_rank * a.push_rows + (row - owner * a.push_rows)) * ld4 + c4;
-        *dst = acc;
-      } else if (a.raw_out == 3) {
-        // node-range tiles of the edge half: this tile's sum joins the earlier tiles' (one
-        // owner per row and launch, so a plain read-modify-write)
-        float4 prev = a.raw[off];
-        hge_f4_add(prev, acc);
-        a.raw[off] = prev;
-      } else {
-        a.raw[off] = acc;
-      }
-      return;
-    }
-    Affine afv;
-    afv.inv = HGE_AF_INV;
-    afv.invlo = HGE_AF_INVLO;
-    const float4 x = finalize_value(yown, acc, degf, invs, afv, gaff);
-    const float w = __frcp_rn(degf);
-    a.yo[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
-    float4 lo4 = HGE_VMIN, hi4 = HGE_VMAX;
-    if (m0) { lo4.x = fminf(lo4.x, x.x); hi4.x = fmaxf(hi4.x, x.x); }
-    if (m1) { lo4.y = fminf(lo4.y, x.y); hi4.y = fmaxf(hi4.y, x.y); }
-    if (m2) { lo4.z = fminf(lo4.z, x.z); hi4.z = fmaxf(hi4.z, x.z); }
-    if (m3) { lo4.w = fminf(lo4.w, x.w); hi4.w = fmaxf(hi4.w, x.w); }
-    HGE_VMIN = lo4;
-    HGE_VMAX = hi4;
-  }
-
-  __device__ __forceinline__ float4 load_own(int row) const {
-    return __ldcs(a.yo + (size_t)row * ld4 + c4);
-  }
-
-  __device__ __forceinline__ static void reduce_groups(float4& v) {
-#pragma unroll
-    for (int off = LPR; off < 32; off <<= 1) {
-      v.x += __shfl_xor_sync(kFull, v.x, off);
-      v.y += __shfl_xor_sync(kFull, v.y, off);
-      v.z += __shfl_xor_sync(kFull, v.z, off);
-      v.w += __shfl_xor_sync(kFull, v.w, off);
-    }
-  }
-
-  // A warp has gathered one chunk of a long row (per-sub-warp sums in acc).  Single-chunk rows
-  // are finished here; multi-chunk rows park the chunk sum, and the last chunk of the row to
-  // arrive adds the parked sums in chunk order (deterministic) and finishes the row.
-  __device__ __forceinline__ void finish_chunk(const HgeHeavyRow& hr, const int2 ch, float4 acc,
-                                               float4 yown) {
-    reduce_groups(acc);
-    if (hr.nchunks == 1) {
-      if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, acc);
-      return;
-    }
-    if (g == 0 && active) __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
-    __threadfence();
-    __syncwarp();
-    int prev = 0;
-    if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
-    prev = __shfl_sync(kFull, prev, 0);
-    if (prev != hr.nchunks - 1) return;
-    __threadfence();
-    if (g == 0 && active && !raw_out) yown = load_own(hr.row);
-    float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
-    for (int k = g; k < hr.nchunks; k += G)
-      if (active)
-        kahan_add(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
-    tot = kahan_result(tot, tcomp);
-    reduce_groups(tot);
-    if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, tot);
-    if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;  // ready for the next launch
-  }
-
-  // Per-column min / max of the rows this block produced: warp shuffles, shared memory, one
-  // atomic per column per block.
-  template <int WARPS>
-  __device__ __forceinline__ void publish_minmax(float4 (*smin)[LPR], float4 (*smax)[LPR]) {
-    if (raw_out) return;    // uniform over the grid
-    float4 lo4 = HGE_VMIN, hi4 = HGE_VMAX;
-#pragma unroll
-    for (int off = LPR; off < 32; off <<= 1) {
-      lo4.x = fminf(lo4.x, __shfl_xor_sync(kFull, lo4.x, off));
-      lo4.y = fminf(lo4.y, __shfl_xor_sync(kFull, lo4.y, off));
-      lo4.z = fminf(lo4.z, __shfl_xor_sync(kFull, lo4.z, off));
-      lo4.w = fminf(lo4.w, __shfl_xor_sync(kFull, lo4.w, off));
-      hi4.x = fmaxf(hi4.x, __shfl_xor_sync(kFull, hi4.x, off));
-      hi4.y = fmaxf(hi4.y, __shfl_xor_sync(kFull, hi4.y, off));
-      hi4.z = fmaxf(hi4.z, __shfl_xor_sync(kFull, hi4.z, off));
-      hi4.w = fmaxf(hi4.w, __shfl_xor_sync(kFull, hi4.w, off));
-    }
-    if (g == 0) {
-      smin[warp][gl] = lo4;
-      smax[warp][gl] = hi4;
-    }
-    __syncthreads();
-    if (threadIdx.x < LPR * 4) {
-      const int l = threadIdx.x >> 2, j = threadIdx.x & 3;
-      const int col = (slab * LPR + l) * 4 + j;
-      if (col < a.R) {
-        const float inf = __int_as_float(0x7f800000);
-        float lo = inf, hi = -inf;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-          lo = fminf(lo, reinterpret_cast<const float*>(&smin[w][l])[j]);
-          hi = fmaxf(hi, reinterpret_cast<const float*>(&smax[w][l])[j]);
-        }
-        if (lo <= hi) {  // this block produced at least one row
-          atomicMin(a.mm_cur + col, hge_enc(lo));
-          atomicMax(a.mm_cur + ld4 * 4 + col, hge_enc(hi));
-        }
-      }
-    }
-  }
-};
-
-template <int LPR>
-__global__ void __launch_bounds__(kBlock, HGE_MIN_BLOCKS) k_half_sweep(const HalfSweepArgs a) {
-  constexpr int G = 32 / LPR;                       // rows per warp on the light path
-  constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;       // idx registers per lane per step of 8
-  constexpr int UR = (LPR >= 8) ? 8 : LPR;          // unroll of a heavy-path round
-
-#if HGE_SMEM_STATE
-  __shared__ float4 s_state[4 * kBlock];
-  RowOwner<LPR> own(a, s_state, kBlock);
-#else
-  RowOwner<LPR> own(a);
-#endif
-  const int lane = own.lane, gl = own.gl, g = own.g, c4 = own.c4, ld4 = own.ld4;
-  const bool active = own.active, raw_out = own.raw_out;
-  const int64_t gw = (int64_t)blockIdx.x * kWarps + own.warp;
-  const int64_t nw = (int64_t)gridDim.x * kWarps;
-  // gathered row c of this lane's column = ygl + c * row_bytes: one 32 x 32 + 64 bit multiply-add
-  // per gather instead of a 64-bit index, a scale and a base-pointer reload (155 -> 105
-  // instructions per round of 8 gathers; profiles/r1_half_sweep_experiments.md)
-  const char* const ygl = reinterpret_cast<const char*>(a.yg + c4);
-  const uint32_t row_bytes = (uint32_t)ld4 * (uint32_t)sizeof(float4);
-  auto gather = [&](int c) -> float4 {
-    return __ldg(reinterpret_cast<const float4*>(ygl + (size_t)(uint32_t)c * row_bytes));
-  };
-
-  // ---- long rows: one warp per chunk of the row --------------------------------------
-  // Loads are software-pipelined: the descriptor of the next chunk and the next block of 32
-  // column ids are requested before the current block's rows are consumed, so a warp pays
-  // one memory latency per block of 32 gathered rows.
-  {
-    int2 ch_next = make_int2(0, 0);
-    if (gw < a.n_chunks) ch_next = __ldcs(a.chunks + gw);
-    for (int64_t ci = gw; ci < a.n_chunks; ci += nw) {
-      const int2 ch = ch_next;
-      if (ci + nw < a.n_chunks) ch_next = __ldcs(a.chunks + ci + nw);
-      const HgeHeavyRow hr = a.hrows[ch.x];
-      const int64_t start = hr.start + (int64_t)ch.y * a.chunk_sz;
-      const int count = min(a.chunk_sz, hr.deg - ch.y * a.chunk_sz);
-      const int32_t* cidx = a.idx + start;
-      float4 yown = hge_f4_zero();
-      if (hr.nchunks == 1 && g == 0 && active && !raw_out) yown = own.load_own(hr.row);
-      float4 acc = hge_f4_zero(), comp = hge_f4_zero();
-      int my = (lane < count) ? __ldcs(cidx + lane) : -1;
-      for (int base = 0; base < count; base += 32) {
-        const int my_next = (base + 32 + lane < count) ? __ldcs(cidx + base + 32 + lane) : -1;
-#pragma unroll
-        for (int r0 = 0; r0 < LPR; r0 += UR) {
-          float4 v[UR];
-#pragma unroll
-          for (int u = 0; u < UR; ++u) {
-            const int c = __shfl_sync(kFull, my, (r0 + u) * G + g);
-            v[u] = (c >= 0 && active) ? gather(c) : hge_f4_zero();
-          }
-          accumulate<UR>(acc, comp, v);
-        }
-        my = my_next;
-      }
-      own.finish_chunk(hr, ch, kahan_result(acc, comp), yown);
-    }
-  }
-
-  // ---- short rows: one sub-warp of LPR lanes per row, G rows per warp -----------------
-  // Two-deep software pipeline over the row descriptors: while the rows of quad q are being
-  // gathered, the descriptor of quad q+2 and the first 8 column ids of quad q+1 are already
-  // in flight, so a quad of short rows costs one memory latency instead of four.
-  {
-    const int4* light4 = reinterpret_cast<const int4*>(a.light);
-    auto load_item = [&](int64_t q) -> int4 {
-      const int64_t i = q * G + g;
-      return (i < a.n_light) ? __ldcs(light4 + i) : make_int4(-1, 0, 0, 0);
-    };
-    auto item_idx = [&](const int4& it) -> const int32_t* {
-      return a.idx + (((int64_t)((uint32_t)it.y >> 8) << 32) | (uint32_t)it.z);
-    };
-    int4 it0 = load_item(gw);
-    int4 it1 = load_item(gw + nw);
-    int cur[K];
-    {
-      const int32_t* ridx = item_idx(it0);
-      const int deg = it0.y & 0xff;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int t = k * LPR + gl;
-        cur[k] = (t < 8 && t < deg) ? __ldcs(ridx + t) : -1;
-      }
-    }
-    for (int64_t q = gw; q * G < a.n_light; q += nw) {
-      const int4 it2 = load_item(q + 2 * nw);
-      int first1[K];
-      {
-        const int32_t* ridx1 = item_idx(it1);
-        const int deg1 = it1.y & 0xff;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int t = k * LPR + gl;
-          first1[k] = (t < 8 && t < deg1) ? __ldcs(ridx1 + t) : -1;
-        }
-      }
-      const int row = it0.x;
-      const bool valid = row >= 0;
-      const int deg = it0.y & 0xff;
-      const float invs = __int_as_float(it0.w);
-      const int32_t* ridx = item_idx(it0);
-      const int maxdeg = __reduce_max_sync(kFull, deg);
-      float4 yown = hge_f4_zero();
-      if (valid && active && !raw_out) yown = own.load_own(row);
-
-      float4 acc = hge_f4_zero(), comp = hge_f4_zero();
-      for (int base = 0; base < maxdeg; base += 8) {
-        int nxt[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int t = base + 8 + k * LPR + gl;
-          nxt[k] = (k * LPR + gl < 8 && t < deg) ? __ldcs(ridx + t) : -1;
-        }
-        float4 v[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int c = __shfl_sync(kFull, cur[(LPR >= 8) ? 0 : t / LPR], (LPR >= 8) ? t : t % LPR, LPR);
-          v[t] = (c >= 0 && active) ? gather(c) : hge_f4_zero();
-        }
-        accumulate<8>(acc, comp, v);
-#pragma unroll
-        for (int k = 0; k < K; ++k) cur[k] = nxt[k];
-      }
-      if (valid && active) own.finish_row(row, (float)deg, invs, yown, kahan_result(acc, comp));
-      it0 = it1;
-      it1 = it2;
-#pragma unroll
-      for (int k = 0; k < K; ++k) cur[k] = first1[k];
-    }
-  }
-
-  __shared__ float4 smin[kWarps][LPR];
-  __shared__ float4 smax[kWarps][LPR];
-  own.template publish_minmax<kWarps>(smin, smax);
 }
 
 // Sharded edge half, second part: the raw sums have been all-reduced over the shards.
@@ -828,29 +383,6 @@ void free_half_schedule(const hge_ctx* ctx, HgeHalfSchedule* s, bool owns_arrays
 
 namespace {
 
-template <int LPR>
-int launch_half(hge_algdist* st, HalfSweepArgs a) {
-  hge_ctx* ctx = st->ctx;
-  dim3 grid(st->grid, st->slabs);
-  k_half_sweep<LPR><<<grid, kBlock, 0, ctx->stream>>>(a);
-  HGE_CHECK_LAUNCH(ctx);
-  return HGE_OK;
-}
-
-template <int LPR>
-int occupancy_grid(const hge_ctx* ctx, int* out) {
-  int per_sm = 0;
-  HGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_half_sweep<LPR>, kBlock, 0));
-  if (per_sm < 1) per_sm = 1;
-  // four waves of blocks rather than one persistent wave: the work list is dealt round-robin, so
-  // blocks of later waves fill the SMs that finish early (long rows make the shares uneven);
-  // measured 0.371 -> 0.353 ms per sweep on config 2
-  per_sm *= 4;
-  if (ctx->blocks_per_sm > 0) per_sm = ctx->blocks_per_sm;
-  *out = per_sm * ctx->num_sms;
-  return HGE_OK;
-}
-
 // Blocks of the stream-fed kernel for one schedule: two waves of resident blocks (a warp owns one
 // contiguous piece; the second wave evens out what the cost model of the pieces gets wrong:
 // 0.399 -> 0.310 ms per sweep on config 2, profiles/r2_half_sweep.md), fewer when there are not
@@ -898,6 +430,8 @@ int run_half_stream(hge_algdist* st, HgeHalfSchedule& s, bool node_half, int swe
   a.push_stage = push ? push->d_peer_stage : nullptr;
   a.push_rows = push ? push->own_rows : 1;
   a.push_rank = push ? push->rank : 0;
+  a.push_map.slice_rows = push ? push->slice_rows : 1;
+  a.push_map.sub_rows = push ? push->sub_rows : 1;
   a.R = st->R;
   a.ld4 = st->ld4;
   return hge_sweep_launch(ctx, a, st->lpr, mode, blocks, st->slabs);
@@ -910,38 +444,7 @@ int run_half(hge_algdist* st, bool node_half, int sweep, float* raw, int slice =
   HgeHalfSchedule& s = tile ? *tile
                        : node_half ? inc->node_half
                                    : (slice >= 0 ? inc->edge_slices[(size_t)slice] : inc->edge_half);
-  if (st->ctx->kernel == 0) return run_half_stream(st, s, node_half, sweep, raw, push, accumulate);
-  HalfSweepArgs a;
-  a.idx = s.idx;
-  a.yg = reinterpret_cast<const float4*>(node_half ? st->ye : st->yn);
-  a.yo = reinterpret_cast<float4*>(node_half ? st->yn : st->ye);
-  a.light = s.light;
-  a.n_light = s.n_light;
-  a.hrows = s.hrows;
-  a.chunks = s.chunks;
-  a.n_chunks = s.n_chunks;
-  a.n_hrows = s.n_hrows;
-  a.chunk_sz = s.chunk_sz;
-  a.partials = st->partials;
-  a.counters = st->counters;
-  a.mm_prev = sweep > 0 ? st->mm + (size_t)(sweep - 1) * 2 * st->ld : nullptr;
-  a.mm_cur = st->mm + (size_t)sweep * 2 * st->ld;
-  a.gather_affine = node_half ? 1 : 0;
-  a.raw_out = push ? 2 : (raw ? (accumulate ? 3 : 1) : 0);
-  a.raw = reinterpret_cast<float4*>(raw);
-  a.push_stage = push ? push->d_peer_stage : nullptr;
-  a.push_rows = push ? push->own_rows : 1;
-  a.push_rank = push ? push->rank : 0;
-  a.R = st->R;
-  a.ld4 = st->ld4;
-  switch (st->lpr) {
-    case 1: return launch_half<1>(st, a);
-    case 2: return launch_half<2>(st, a);
-    case 4: return launch_half<4>(st, a);
-    case 8: return launch_half<8>(st, a);
-    case 16: return launch_half<16>(st, a);
-    default: return launch_half<32>(st, a);
-  }
+  return run_half_stream(st, s, node_half, sweep, raw, push, accumulate);
 }
 
 }  // namespace
@@ -1317,15 +820,6 @@ int hge_algdist_create(hge_ctx* ctx, hge_incidence* inc, int R, int max_iteratio
     hge_set_error("hge_algdist_create: memset failed");
     return fail(HGE_ERR_CUDA);
   }
-  switch (st->lpr) {
-    case 1: rc = occupancy_grid<1>(ctx, &st->grid); break;
-    case 2: rc = occupancy_grid<2>(ctx, &st->grid); break;
-    case 4: rc = occupancy_grid<4>(ctx, &st->grid); break;
-    case 8: rc = occupancy_grid<8>(ctx, &st->grid); break;
-    case 16: rc = occupancy_grid<16>(ctx, &st->grid); break;
-    default: rc = occupancy_grid<32>(ctx, &st->grid); break;
-  }
-  if (rc != HGE_OK) return fail(rc);
   if ((rc = hge_sweep_resident_blocks(st->lpr, &st->sweep_resident)) != HGE_OK) return fail(rc);
   *out = st;
   return HGE_OK;
@@ -1439,19 +933,60 @@ int hge_algdist_edge_finalize(hge_algdist* st, int sweep, int slice, const float
   return HGE_OK;
 }
 
-int hge_internal_edge_push(hge_algdist* st, int sweep) {
-  if (!st->tile_raw) return run_half(st, false, sweep, nullptr, -1, st->p2p);
-  // tiled: the local partial sums are accumulated tile by tile, then pushed to their owners
+// The sharded edge gather with the partial rows pushed to their owners: slice >= 0 gathers only
+// that slice of the edge rows (the pipelined peer-memory sweep), slice < 0 all of them.
+int hge_internal_edge_push(hge_algdist* st, int sweep, int slice) {
+  hge_p2p* p = st->p2p;
+  if (!st->tile_raw) {
+    HgeHalfSchedule* sched = slice >= 0 ? &p->slice_sched[(size_t)slice] : nullptr;
+    return run_half(st, false, sweep, nullptr, -1, p, sched);
+  }
+  // tiled: the local partial sums are accumulated tile by tile, then pushed to their owners (in
+  // one piece: the tiles already walk all edges, there is nothing to pipeline the exchange with)
   hge_ctx* ctx = st->ctx;
   hge_incidence* inc = st->inc;
-  const hge_p2p* p = st->p2p;
+  HGE_REQUIRE(slice < 0, "hge_internal_edge_push: the tiled edge half is not sliced");
   HGE_CUDA(cudaMemsetAsync(st->tile_raw, 0, (size_t)inc->E * st->ld * sizeof(float), ctx->stream));
   for (size_t t = 0; t < inc->edge_tiles.size(); ++t)
     HGE_TRY(run_half(st, false, sweep, st->tile_raw, -1, nullptr, &inc->edge_tiles[t], true));
+  HgeOwnerMap map;
+  map.slice_rows = p->slice_rows;
+  map.sub_rows = p->sub_rows;
   k_push_rows<<<grid_1d(ctx, (int64_t)inc->E * st->ld4, kBlock), kBlock, 0, ctx->stream>>>(
-      inc->E, st->ld4, reinterpret_cast<const float4*>(st->tile_raw), p->d_peer_stage, p->own_rows,
-      p->rank);
+      0, inc->E, st->ld4, reinterpret_cast<const float4*>(st->tile_raw), p->d_peer_stage, p->own_rows,
+      p->rank, map);
   HGE_CHECK_LAUNCH(ctx);
+  return HGE_OK;
+}
+
+// Builds the per-slice schedules of a shard's edge half (hge_algdist_attach_p2p).
+int hge_internal_slice_schedules(hge_algdist* st) {
+  hge_p2p* p = st->p2p;
+  hge_incidence* inc = st->inc;
+  hge_ctx* ctx = st->ctx;
+  for (HgeHalfSchedule& sl : p->slice_sched) hge_sched_release(ctx, &sl);
+  p->slice_sched.clear();
+  if (p->slices <= 1 || st->tile_raw) return HGE_OK;
+  p->slice_sched.resize((size_t)p->slices);
+  for (int k = 0; k < p->slices; ++k) {
+    const int32_t r0 = (int32_t)std::min<int64_t>((int64_t)k * p->slice_rows, inc->E);
+    const int32_t r1 = (int32_t)std::min<int64_t>((int64_t)(k + 1) * p->slice_rows, inc->E);
+    HGE_TRY(hge_sched_begin(ctx, r0, r1, inc->e2n_ptr, inc->N, &p->slice_sched[(size_t)k]));
+  }
+  size_t n_part = 0, n_cnt = 0;
+  for (HgeHalfSchedule& sl : p->slice_sched) {
+    sl.idx = inc->edge_half.idx;
+    sl.deg = inc->edge_half.deg;
+    sl.invs = inc->edge_half.invs;
+    HGE_TRY(hge_sched_finish(ctx, "edge", &sl));
+    n_part = std::max(n_part, (size_t)sl.n_partials);
+    n_cnt = std::max(n_cnt, (size_t)sl.n_hrows);
+  }
+  // the parked chunk sums / arrival counters were sized for the whole-half schedules; a slice
+  // never needs more (it has a subset of the long rows), but make that explicit
+  HGE_REQUIRE(n_part <= (size_t)std::max(inc->node_half.n_partials, inc->edge_half.n_partials) &&
+                  n_cnt <= (size_t)std::max(inc->node_half.n_hrows, inc->edge_half.n_hrows),
+              "hge_internal_slice_schedules: slice schedule larger than the whole");
   return HGE_OK;
 }
 

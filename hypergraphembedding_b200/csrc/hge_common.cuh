@@ -50,8 +50,8 @@ struct hge_ctx {
   int light_max_deg;
   int chunk;
   int blocks_per_sm;
-  int kernel;            // 0: k_sweep over the packed gather stream, 1: k_half_sweep over work items
   int unit_cost;         // per-unit cost in steps when the stream is cut into pieces
+  int p2p_slices;        // default number of slices the peer-memory exchange is pipelined in
   int tile_mb;           // node-range tile of the single-GPU edge half in MB of rows (0 = off)
   int tile_min_mb;       // ... used when the node rows exceed this many MB
   int tile_force;        // min_rows_mb == 0 (tests): tile whatever the edge sizes are

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 
 #include "hge_common.cuh"
@@ -65,14 +66,13 @@ static void set_default_tuning(hge_ctx* ctx) {
   ctx->light_max_deg = 128;
   ctx->chunk = 1024;
   ctx->blocks_per_sm = 0;  // 0: 4 x what the occupancy calculator says is resident
-  // half-sweep kernel: 0 = k_sweep over the packed gather stream (csrc/hge_sweep.cu), 1 = the
-  // first-generation k_half_sweep over the CSR work items (kept for A/B measurements)
-  ctx->kernel = 0;
-  if (const char* env = getenv("HGE_KERNEL")) ctx->kernel = strcmp(env, "items") == 0 ? 1 : 0;
   // cost of a unit (a chunk of a long row, a group of short rows) in steps of 4 gathers, used to
   // cut the stream into pieces of equal cost
   ctx->unit_cost = 1;
   if (const char* env = getenv("HGE_UNIT_COST")) ctx->unit_cost = atoi(env);
+  // peer-memory exchange of the sharded edge half: pipelined in this many slices of edge rows
+  ctx->p2p_slices = 4;
+  if (const char* env = getenv("HGE_P2P_SLICES")) ctx->p2p_slices = std::max(1, std::min(16, atoi(env)));
   // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
   // the edge half over more than 512 MB of node rows is tiled by node range into L2-sized tiles
   // when the edges are large enough for that to pay (profiles/r1_tiled_edge_half.md)
@@ -194,16 +194,6 @@ int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb) {
   ctx->tile_mb = tile_mb;
   ctx->tile_min_mb = min_rows_mb;
   ctx->tile_force = min_rows_mb == 0;
-  return HGE_OK;
-}
-
-int hge_ctx_set_kernel(hge_ctx* ctx, int kernel, int unit_cost) {
-  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_kernel: ctx is NULL");
-  HGE_REQUIRE(kernel == 0 || kernel == 1, "hge_ctx_set_kernel: kernel %d not in {0, 1}", kernel);
-  HGE_REQUIRE(unit_cost >= 0 && unit_cost <= 1024, "hge_ctx_set_kernel: unit_cost %d not in [0, 1024]",
-              unit_cost);
-  ctx->kernel = kernel;
-  if (unit_cost) ctx->unit_cost = unit_cost;
   return HGE_OK;
 }
 

@@ -139,7 +139,11 @@ struct hge_incidence {
 struct hge_p2p {
   hge_ctx* ctx = nullptr;
   int rank = 0, world = 1;
-  int32_t E = 0, N = 0, ld = 0, own_rows = 0;   // own_rows = ceil(E / world); N = local node rows
+  int32_t E = 0, N = 0, ld = 0;                // N = local node rows
+  // Ownership of the edge rows: the rows are cut into `slices` slices of slice_rows consecutive
+  // rows (the unit the exchange is pipelined in), every slice into `world` runs of sub_rows rows,
+  // run o of every slice belongs to rank o.  own_rows = slices * sub_rows rows per rank.
+  int32_t slices = 1, slice_rows = 0, sub_rows = 0, own_rows = 0;
   char* base = nullptr;                      // local arena
   size_t off_ye = 0, off_stage = 0, off_mmx = 0, off_flags = 0, off_err = 0, off_yn = 0, bytes = 0;
   char* peer_base[16] = {nullptr};           // peer arenas (own slot = base)
@@ -150,6 +154,24 @@ struct hge_p2p {
   uint32_t** d_peer_flags = nullptr;
   uint32_t seq = 0;                          // barrier sequence number (same on every rank)
   bool peers_open = false;
+  // pipelined exchange: slice k's barrier + owner-side reduce run on `side` while slice k + 1 is
+  // gathered on the context's stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t gathered[16] = {nullptr};
+  cudaEvent_t reduced = nullptr;
+  std::vector<HgeHalfSchedule> slice_sched;  // the shard's edge half, one schedule per slice
+};
+
+// (owner rank, row inside the owner's block) of an edge row -- shared by the kernels that push
+// partial rows to their owners and by the owner-side reduce
+struct HgeOwnerMap {
+  int32_t slice_rows, sub_rows;
+  __host__ __device__ void locate(int32_t row, int& owner, int32_t& idx) const {
+    const int32_t k = row / slice_rows;
+    const int32_t w = row - k * slice_rows;
+    owner = w / sub_rows;
+    idx = k * sub_rows + (w - owner * sub_rows);
+  }
 };
 
 // Relaxation state (csrc/hge_algdist.cu).
@@ -172,5 +194,7 @@ struct hge_algdist {
   hge_p2p* p2p = nullptr;
 };
 
-// internal: the sharded edge gather with the partial rows pushed to their owners
-extern "C" int hge_internal_edge_push(hge_algdist* st, int sweep);
+// internal: the sharded edge gather with the partial rows pushed to their owners (slice < 0: all
+// edge rows), and the per-slice schedules it runs over
+extern "C" int hge_internal_edge_push(hge_algdist* st, int sweep, int slice);
+extern "C" int hge_internal_slice_schedules(hge_algdist* st);

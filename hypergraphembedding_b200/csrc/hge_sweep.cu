@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     const size_t off = (size_t)row * ld4 + c4;
     if (MODE == kSweepPush) {
       // fused reduce-scatter: the partial row goes straight into the owning GPU's staging block
-      const int owner = row / a.push_rows;
-      float4* dst = a.push_stage[owner] +
-                    ((size_t)a.push_rank * a.push_rows + (row - owner * a.push_rows)) * ld4 + c4;
+      int owner;
+      int32_t idx;
+      a.push_map.locate(row, owner, idx);
+      float4* dst = a.push_stage[owner] + ((size_t)a.push_rank * a.push_rows + idx) * ld4 + c4;
       *dst = acc;
     } else if (MODE == kSweepRawAdd) {
       float4 prev = a.raw[off];

@@ -29,8 +29,9 @@ struct HgeSweepArgs {
   int32_t* mm_cur;             // min / max slots of this sweep
   float4* raw;
   float4* const* push_stage;   // kSweepPush: staging blocks of all ranks
-  int32_t push_rows;           //   rows owned per rank
+  int32_t push_rows;           //   rows owned per rank (= rows per source rank in a staging block)
   int32_t push_rank;
+  HgeOwnerMap push_map;        //   edge row -> (owner, row inside the owner's block)
   int32_t R;
   int32_t ld4;
 };

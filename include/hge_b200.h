@@ -62,12 +62,6 @@ int hge_ctx_sync(hge_ctx* ctx);
  *   chunk          incidences per warp work item for longer rows (default 1024)
  *   blocks_per_sm  grid size = SMs * blocks_per_sm (default: 4 x the resident blocks) */
 int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_per_sm);
-/* Half-sweep kernel selection (A/B measurements; results differ only by fp32 summation order):
- *   kernel     0 = k_sweep, fed by a packed gather stream laid out in consumption order (default);
- *              1 = the first-generation k_half_sweep over 16-byte CSR work items
- *   unit_cost  cost of one unit of work in steps of 4 gathers when the stream is cut into
- *              equal-cost pieces, one per warp (0 keeps the default of 1) */
-int hge_ctx_set_kernel(hge_ctx* ctx, int kernel, int unit_cost);
 /* Edge half over node rows that exceed what random 128-byte gathers reach at full rate
  * (measured on config 5: 1.9 TB/s over 8.3 GB of rows, 4.9 TB/s inside 1 GB, 6.3 TB/s inside an
  * L2-sized block): when the (local) node rows exceed min_rows_mb megabytes the half-sweep runs
@@ -170,8 +164,11 @@ int hge_algdist_store(hge_algdist* st, int sweeps_done, float* xn, float* xe, in
  * call the same sequence of sweeps; each rank must drive its own GPU.  A barrier that is not
  * met within 20 s raises an error flag (hge_p2p_check) instead of hanging. */
 typedef struct hge_p2p hge_p2p;
+/* num_local_nodes: this rank's node rows (they live in the arena next to the edge rows, though no
+ * peer touches them).  slices: the exchange is pipelined in this many slices of edge rows -- slice
+ * k's barrier and owner-side reduce overlap the gather of slice k + 1 (0 = default, 4; 1 = off). */
 int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, int32_t num_edges,
-                   int ld, hge_p2p** out);
+                   int ld, int slices, hge_p2p** out);
 int hge_p2p_export(hge_p2p* p, void* handle64);
 int hge_p2p_open_peers(hge_p2p* p, const void* handles /* world x 64 bytes */);
 int hge_p2p_check(hge_p2p* p);

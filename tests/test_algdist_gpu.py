@@ -138,10 +138,9 @@ def test_tuning_knobs_do_not_change_results(gpu_ctx):
     gpu_ctx.reset_tuning()      # the library's own defaults, not a copy of them
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
-def test_both_half_sweep_kernels_against_the_oracle(kernel, gpu_ctx):
-  """The stream-fed k_sweep (default) and the first-generation k_half_sweep on a graph with
-  short rows, single-chunk and multi-chunk long rows, R not a multiple of 4."""
+def test_short_rows_single_and_multi_chunk_long_rows_against_the_oracle(gpu_ctx):
+  """A graph with short rows, single-chunk and multi-chunk long rows on both sides, R a multiple
+  of 4 and not (lanes beyond the row, padding columns)."""
   from oracle import port
   rng = np.random.default_rng(17)
   n, e = 9000, 400
@@ -154,11 +153,7 @@ def test_both_half_sweep_kernels_against_the_oracle(kernel, gpu_ctx):
     xn0 = rng.random((n, R)).astype(np.float32)
     xe0 = rng.random((e, R)).astype(np.float32)
     ref_xn, ref_xe = port.algdist_vectorised(A, A.T.tocsr(), xn0, xe0, 6)
-    try:
-      gpu_ctx.set_kernel(kernel)
-      xn, xe = _run(A, xn0, xe0, 6, gpu_ctx)
-    finally:
-      gpu_ctx.reset_tuning()
+    xn, xe = _run(A, xn0, xe0, 6, gpu_ctx)
     assert_distance_parity(A, xn, xe, ref_xn, ref_xe)
 
 

@@ -17,4 +17,3 @@ for f in $V/libhge_*.so; do
   [ -e "$f" ] || continue
   run "$(basename $f)" HGE_LIB_PATH=$f --
 done
-run items HGE_KERNEL=items --
