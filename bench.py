@@ -335,6 +335,56 @@ def hobe_extra(ctx):
           "fobe_records": len(fobe), "fobe_samples_per_s": len(fobe) / fobe_s}
 
 
+def hobe_scale_extra(ctx):
+  """HOBE weighted samples/s where the number means something: the 100 000-node member of the
+  config-4 family (485 K incidences... see `workload`), num_neighbors 5, num_samples 20, R = 10.
+  Split into the sequential replay of numpy's RNG stream on the host and the probability kernels
+  on the device; pair sets, neighbour arrays and RNG state are checked against the committed
+  digest of the scipy / numpy oracle (tests/golden/hobe_scale.npz), probabilities on a stride."""
+  import hashlib
+  import hypergraphembedding_b200 as H
+  from hypergraphembedding_b200 import synthetic
+  path = os.path.join(ROOT, "tests", "golden", "hobe_scale.npz")
+  if not os.path.exists(path):
+    return {"error": "tests/golden/hobe_scale.npz is missing"}
+  g = np.load(path)
+  A = synthetic.zipf_hypergraph(int(g["nodes"]), int(g["edges"]), seed=int(g["graph_seed"]))
+  xn, xe = synthetic.legacy_initial_vectors(A.shape[0], A.shape[1], int(g["R"]), seed=int(g["vec_seed"]))
+  k, num_samples = int(g["k"]), int(g["num_samples"])
+
+  def sha(cols):
+    h = hashlib.sha256()
+    for c in cols:
+      h.update(np.ascontiguousarray(c, dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+  best, split, out = None, None, None
+  for _ in range(3):
+    np.random.seed(int(g["seed"]))
+    timings = {}
+    t = time.perf_counter()
+    out = H.AlgebraicDistanceSamplesCsr(A, xn, xe, k, num_samples, timings=timings)
+    dt = time.perf_counter() - t
+    if best is None or dt < best:
+      best, split = dt, timings
+  prob = np.where(~np.isnan(out.nn_prob), out.nn_prob,
+                  np.where(~np.isnan(out.ee_prob), out.ee_prob, out.ne_prob))
+  want = g["prob_strided"]
+  got = prob[::int(g["stride"])]
+  return {"workload": "synthetic Zipf hypergraph %d nodes / %d edges / %d incidences (config-4 family), R=%d, "
+                      "num_neighbors=%d, num_samples=%d" % (A.shape[0], A.shape[1], A.nnz, int(g["R"]), k,
+                                                            num_samples),
+          "records": len(out), "seconds": best, "samples_per_s": len(out) / best,
+          "host_rng_replay_s": split["draw"], "gpu_probabilities_s": split["probabilities"],
+          "incidence_weights_s": split["weights"],
+          "pair_sets_bit_exact": bool(len(out) == int(g["count"]) and
+                                      sha([out.left_node, out.left_edge, out.right_node, out.right_edge]) ==
+                                      str(g["index_sha"])),
+          "neighbours_bit_exact": bool(sha([out.neigh_node, out.neigh_edge]) == str(g["neigh_sha"])),
+          "max_prob_err_over_bound": float((np.abs(got - want) / (1e-5 * np.abs(want) + 1e-6)).max()),
+          "unit": "weighted samples/s (CSR + dense vectors in, columnar records out)"}
+
+
 def hg2v_train_extra(ctx, dimension=32, epochs=3):
   """The consumer of the HOBE sample columns: UnweightedFloatModel (hg2v_model.py:129-203) trained
   on the 755 267 configs[0] records with the reference's fit settings (batch 256, Adagrad;
@@ -659,7 +709,7 @@ def run_ours(args, spec):
     inc.close()
     del a_ptr, a_idx, b_ptr, b_idx, xn, xe, xn_init, xe_init
     torch.cuda.empty_cache()
-    for key, fn in (("hobe", hobe_extra), ("hg2v_train", hg2v_train_extra),
+    for key, fn in (("hobe", hobe_extra), ("hobe_scale", hobe_scale_extra), ("hg2v_train", hg2v_train_extra),
                     ("c1_end_to_end", c1_end_to_end_extra),
                     ("pair_weighting", pair_weighting_extra),
                     ("c5", lambda c: c5_extra(args, 1, 0, local_rank, c))):

@@ -10,7 +10,8 @@ from .hypergraph_pb2 import (EvaluationMetrics, ExperimentalResult, Hypergraph,
 from .hypergraph_util import (AddNodeToEdge, CompressRange, IsEmpty, Relabel, ToCsrMatrix,
                               ToEdgeCsrMatrix)
 from .algebraic_distance import EmbedAlgebraicDistance
-from .hg2v_sample import (AlgebraicDistanceSamples, BooleanSamples, BooleanSamplesCsr,
+from .hg2v_sample import (AlgebraicDistanceSamples, AlgebraicDistanceSamplesCsr, BooleanSamples,
+                          BooleanSamplesCsr,
                           SampleColumns, SamplesToModelInput, SimilarityRecord,
                           SparseWeightedJaccard, WeightedJaccardSamples)
 from .hg2v_model import BooleanModel, KerasModelToEmbedding, UnweightedFloatModel
@@ -25,7 +26,8 @@ __all__ = [
     "Hypergraph", "HypergraphEmbedding", "EvaluationMetrics", "ExperimentalResult",
     "AddNodeToEdge", "CompressRange", "IsEmpty", "Relabel", "ToCsrMatrix", "ToEdgeCsrMatrix",
     "EmbedAlgebraicDistance",
-    "AlgebraicDistanceSamples", "BooleanSamples", "BooleanSamplesCsr", "SampleColumns",
+    "AlgebraicDistanceSamples", "AlgebraicDistanceSamplesCsr", "BooleanSamples", "BooleanSamplesCsr",
+    "SampleColumns",
     "SamplesToModelInput", "SimilarityRecord", "SparseWeightedJaccard", "WeightedJaccardSamples",
     "BooleanModel", "UnweightedFloatModel", "KerasModelToEmbedding", "EMBEDDING_OPTIONS",
     "EmbedHg2vBoolean", "EmbedHg2vAdjJaccard", "EmbedHg2vNeighborhoodWeightedJaccard",

@@ -604,36 +604,65 @@ def AlgebraicDistanceSamples(hypergraph, algebraic_embedding, num_neighbors, num
   assert num_samples >= 0
 
   g = _Graph(hypergraph)
-  k = num_neighbors
   xn, xe = embedding_to_arrays(algebraic_embedding, g.num_nodes, g.num_edges)
-  weights = _HobeWeights(g, xn, xe)
+  return _hobe_samples(g, xn, xe, num_neighbors, num_samples)
+
+
+def AlgebraicDistanceSamplesCsr(incidence, xn, xe, num_neighbors, num_samples, timings=None):
+  """AlgebraicDistanceSamples on an N x E incidence given as a scipy CSR matrix and dense fp32
+  vector blocks [N, R], [E, R] -- the form a caller at scale holds (building the proto alone
+  takes longer than the sampling; cf. BooleanSamplesCsr).  Same records, same consumption of the
+  global numpy RNG.  `timings` (a dict) receives the seconds spent replaying the RNG stream on
+  the host ("draw") and computing probabilities on the device ("probabilities")."""
+  assert num_neighbors >= 0
+  assert num_samples >= 0
+  g = incidence if isinstance(incidence, _Graph) else _Graph.from_csr(incidence)
+  xn = np.ascontiguousarray(xn, dtype=np.float32)
+  xe = np.ascontiguousarray(xe, dtype=np.float32)
+  assert xn.shape[0] == g.num_nodes and xe.shape[0] == g.num_edges and xn.shape[1] == xe.shape[1]
+  return _hobe_samples(g, xn, xe, num_neighbors, num_samples, timings)
+
+
+def _hobe_samples(g, xn, xe, k, num_samples, timings=None):
+  import time
+  spent = {"draw": 0.0, "probabilities": 0.0, "weights": 0.0}
+
+  def timed(kind, fn, *args):
+    t = time.perf_counter()
+    out = fn(*args)
+    spent[kind] += time.perf_counter() - t
+    return out
+
+  weights = timed("weights", _HobeWeights, g, xn, xe)
   try:
     state = _native.LegacyRngState()
     parts = []
     log.info("Getting node-node samples")
     per_node = [num_samples] * len(g.node_rows)
     per_edge = [num_samples] * len(g.edge_rows)
-    r, c = _native.sample_adj_rows((g.a, g.at), g.node_rows, per_node, state)
+    r, c = timed("draw", _native.sample_adj_rows, (g.a, g.at), g.node_rows, per_node, state)
     log.info("Sampling node-node probabilities")
     parts.append(SampleColumns.build(k, len(r), left_node=r, right_node=c,
-                                     nn_prob=weights.same_type(0, r, c)))
+                                     nn_prob=timed("probabilities", weights.same_type, 0, r, c)))
     log.info("Getting edge-edge samples")
-    r, c = _native.sample_adj_rows((g.b, g.bt), g.edge_rows, per_edge, state)
+    r, c = timed("draw", _native.sample_adj_rows, (g.b, g.bt), g.edge_rows, per_edge, state)
     log.info("Sampling edge-edge probabilities")
     parts.append(SampleColumns.build(k, len(r), left_edge=r, right_edge=c,
-                                     ee_prob=weights.same_type(1, r, c)))
+                                     ee_prob=timed("probabilities", weights.same_type, 1, r, c)))
     log.info("Getting node-edge samples")
-    n1, e1 = _native.sample_adj_rows((g.a, g.at, g.a), g.node_rows, per_node, state)
+    n1, e1 = timed("draw", _native.sample_adj_rows, (g.a, g.at, g.a), g.node_rows, per_node, state)
     log.info("Getting edge-node samples")
-    e2, n2 = _native.sample_adj_rows((g.b, g.bt, g.b), g.edge_rows, per_edge, state)
+    e2, n2 = timed("draw", _native.sample_adj_rows, (g.b, g.bt, g.b), g.edge_rows, per_edge, state)
     state.commit()   # the parent's stream ends here (workers draw from a copy)
     nodes, edges = np.concatenate([n1, n2]), np.concatenate([e1, e2])
-    nbr_e, nbr_n = _native.sample_neighbors(g.a, g.b, nodes, edges, k, state.copy())
+    nbr_e, nbr_n = timed("draw", _native.sample_neighbors, g.a, g.b, nodes, edges, k, state.copy())
     parts.append(SampleColumns.build(k, len(nodes), left_node=nodes, right_edge=edges,
                                      neigh_node=nbr_n, neigh_edge=nbr_e,
-                                     ne_prob=weights.diff_type(nodes, edges)))
+                                     ne_prob=timed("probabilities", weights.diff_type, nodes, edges)))
   finally:
     weights.close()
+  if timings is not None:
+    timings.update(spent)
   return SampleColumns.concatenate(parts)
 
 

@@ -58,6 +58,8 @@ def load_reference():
   pkg.__path__ = [os.path.join(REFERENCE_ROOT, "hypergraph_embedding")]
   pkg.Hypergraph = pb.Hypergraph
   pkg.HypergraphEmbedding = pb.HypergraphEmbedding
+  pkg.EvaluationMetrics = pb.EvaluationMetrics
+  pkg.ExperimentalResult = pb.ExperimentalResult
   pb2 = types.ModuleType("hypergraph_embedding.hypergraph_pb2")
   pb2.Hypergraph = pb.Hypergraph
   pb2.HypergraphEmbedding = pb.HypergraphEmbedding
@@ -85,3 +87,20 @@ def load_reference():
     setattr(ns, name, importlib.import_module("hypergraph_embedding." + name))
   _loaded = ns
   return ns
+
+
+def load_reference_evaluation():
+  """The reference's ``evaluation_util`` module (evaluation_util.py:1-590).  It imports keras at
+  module scope for one predictor that nothing here calls; keras is absent, so attribute-free
+  stub modules stand in for it."""
+  load_reference()
+  for name in ("keras", "keras.models", "keras.layers", "keras.callbacks"):
+    if name not in sys.modules:
+      try:
+        importlib.import_module(name)
+      except ImportError:
+        stub = types.ModuleType(name)
+        for attr in ("Model", "Input", "Dense", "EarlyStopping"):
+          setattr(stub, attr, None)
+        sys.modules[name] = stub
+  return importlib.import_module("hypergraph_embedding.evaluation_util")
