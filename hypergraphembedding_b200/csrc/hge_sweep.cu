@@ -42,6 +42,12 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef HGE_SWEEP_AFFINE_REGS
 #define HGE_SWEEP_AFFINE_REGS 0
 #endif
+// bit 0: the node half stores its rows with the streaming (evict-first) hint, bit 1: the edge half
+// does.  The rows a half writes compete for L2 with the table it gathers from; measured on
+// config 2 (profiles/r2_half_sweep.md): 0.3069 -> 0.3042 ms per sweep with both.
+#ifndef HGE_SWEEP_STORE_CS
+#define HGE_SWEEP_STORE_CS 3
+#endif
 // measurement-only builds (wrong results): 1 = finished rows are dropped, 2 = ids are not
 // broadcast inside the lane group, 4 = descriptors are not read
 #ifndef HGE_SWEEP_DEBUG
@@ -254,7 +260,11 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
         x.w = fmaf(inv.w * hd, yown.w, fmaf(hs, acc.w, -c3.w));
       }
       const float w = __frcp_rn(degf);
-      a.own[off] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
+      const float4 y = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
+      if ((MODE == kSweepNode && (HGE_SWEEP_STORE_CS & 1)) || (MODE == kSweepEdge && (HGE_SWEEP_STORE_CS & 2)))
+        __stcs(a.own + off, y);
+      else
+        a.own[off] = y;
       // padding columns (>= R) stay 0 and are not published, so no per-column mask here
 #if HGE_SWEEP_MINMAX_REGS
       rmin.x = fminf(rmin.x, x.x); rmax.x = fmaxf(rmax.x, x.x);

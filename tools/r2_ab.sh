@@ -13,6 +13,7 @@ run() { # name, env..., -- tuning args
   env "${envs[@]}" timeout 600 python tools/time_variant.py c2 "$@" 2>&1 | tail -1
 }
 run default X=1 --
+run default_again X=1 --
 for f in $V/libhge_*.so; do
   [ -e "$f" ] || continue
   run "$(basename $f)" HGE_LIB_PATH=$f --
