@@ -104,13 +104,17 @@ def compulsory_bytes_per_launch(N, E, nnz, R):
   return (2 * nnz * 4 + 3 * (N + E) * 4 * R) / 2.0
 
 
-def kernel_source_sha():
-  """Hash of the CUDA sources: an ncu capture is only quoted next to the kernels it measured."""
-  import glob
+# the sources that define the half-sweep kernel and the gather stream it reads
+HALF_SWEEP_SOURCES = ("hge_sweep.cu", "hge_sweep.cuh", "hge_schedule.cu", "hge_incidence.cuh", "hge_common.cuh")
+
+
+def kernel_source_sha(files=HALF_SWEEP_SOURCES):
+  """Hash of the CUDA sources of a kernel: an ncu capture is only quoted next to the kernel it
+  measured."""
   import hashlib
   h = hashlib.sha256()
-  for path in sorted(glob.glob(os.path.join(ROOT, "hypergraphembedding_b200", "csrc", "*.cu*"))):
-    h.update(open(path, "rb").read())
+  for name in sorted(files):
+    h.update(open(os.path.join(ROOT, "hypergraphembedding_b200", "csrc", name), "rb").read())
   return h.hexdigest()[:16]
 
 

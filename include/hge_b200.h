@@ -234,9 +234,11 @@ int hge_diff_type_prob(hge_ctx* ctx, hge_incidence* inc, const float* w_e2n, con
                        const int32_t* pe, int64_t num_pairs, float* prob, int mem);
 
 /* ---- sparse weighted Jaccard (WeightedJaccardSamples, hg2v_sample.py:250-510) -----------
- * Feature matrices are CSR with int64 row pointers, sorted int32 column ids and fp32 values
- * >= 0 (negative values: HGE_ERR_UNSUPPORTED).  J(x, y) = sum min / sum max over the union of
- * the non-zeros, 0 when the denominator is 0 (SparseWeightedJaccard, :250-275). */
+ * Feature matrices are CSR with int64 row pointers, sorted int32 column ids and fp32 values.
+ * J(x, y) = sum min / sum max over the union of the non-zeros, 0 when the denominator is 0
+ * (SparseWeightedJaccard, :250-275).  Both sums are carried in fp32 in the reference's own order
+ * (ascending column, one value at a time), so the result equals the reference's bit for bit on
+ * fp32 features. */
 
 /* out[p] = J(F[pi[p]], F[pj[p]]): SameTypeJaccardSample (:323-340). */
 int hge_jaccard_rows(hge_ctx* ctx, const int64_t* ptr, const int32_t* idx, const float* val,
@@ -244,9 +246,10 @@ int hge_jaccard_rows(hge_ctx* ctx, const int64_t* ptr, const int32_t* idx, const
                      int64_t num_pairs, float* out, int mem);
 
 /* out[p] = J(X[px[p]], mean_{t in G[pg[p]]} F[t]): one factor of DiffTypeJaccardSample
- * (:343-392) without materialising the centroids of CentroidFromRows / GetAllCentroids
- * (:284-320).  G is a boolean CSR (group -> member rows of F); X and F have the same number of
- * columns (X may be F itself).  An empty group gives 0. */
+ * (:343-392).  The centroid rows of the groups the pairs name are materialised on the device the
+ * way CentroidFromRows (:284-299) computes them (members added in ascending order in fp32, one
+ * division by the group size).  G is a boolean CSR (group -> member rows of F); X and F have the
+ * same number of columns (X may be F itself).  An empty group gives 0. */
 int hge_jaccard_centroid(hge_ctx* ctx, const int64_t* xptr, const int32_t* xidx, const float* xval,
                          int64_t xrows, int64_t xnnz, const int64_t* gptr, const int32_t* gidx,
                          int64_t grows, int64_t gnnz, const int64_t* fptr, const int32_t* fidx,

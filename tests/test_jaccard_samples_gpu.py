@@ -1,7 +1,8 @@
-"""WeightedJaccardSamples (HG2V_ADJ_JAC / HG2V_NEIGH_JAC, hg2v_sample.py:250-510): pair sets and
-neighbour arrays bit-exact, Jaccard probabilities and left / right weights within 1e-5 of the
-unmodified reference (committed golden outputs, oracle/make_golden.py --only jaccard), plus the
-reference's own known-answer vectors (tests/test_hg2v_samples.py:192-304)."""
+"""WeightedJaccardSamples (HG2V_ADJ_JAC / HG2V_NEIGH_JAC, hg2v_sample.py:250-510): pair sets,
+neighbour arrays AND the Jaccard probabilities / left / right weights bit for bit equal to the
+unmodified reference (committed golden outputs, oracle/make_golden.py --only jaccard) -- the
+kernels carry the two sums in the reference's own order -- plus the reference's own known-answer
+vectors (tests/test_hg2v_samples.py:192-304)."""
 import hashlib
 
 import numpy as np
@@ -72,16 +73,15 @@ def test_weighted_jaccard_samples_match_reference(name):
     assert np.array_equal(np.isnan(arrays[k]), np.isnan(g["col_" + k])), k
     got, want = np.nan_to_num(arrays[k]), np.nan_to_num(g["col_" + k])
     assert np.all((got >= 0) & (got <= 1 + ATOL))
-    # The bar: 1e-5 relative to the reference.  The reference adds its minima / maxima one by
-    # one in fp32 (hg2v_sample.py:262-271), which on rows with thousands of non-zeros is itself
-    # only good to a few 1e-6; where the bar is missed the result must be at least as close to
-    # the float64 value of the same formula as the reference's own number is.
-    close = np.abs(got - want) <= RTOL * np.abs(want) + ATOL
+    # The reference adds its minima / maxima one by one in fp32 in ascending column order
+    # (hg2v_sample.py:262-271) and builds centroids with scipy's column sums (members ascending,
+    # fp32); the kernels do the same, so every record is the reference's number exactly.
+    assert np.array_equal(got.astype(np.float32), want.astype(np.float32)), \
+        (k, int((got != want).sum()), float(np.abs(got - want).max()))
+    # ... and stays as close to the float64 value of the same formula as one-by-one fp32 sums over
+    # rows of thousands of non-zeros get (the reference's own accuracy: a few 1e-6 absolute)
     exact = np.nan_to_num(truth[k])
-    better = np.abs(got - exact) <= np.abs(want - exact) + 1e-7
-    assert np.all(close | better), (k, np.abs(got - want).max())
-    assert np.all(np.abs(got - exact) <= RTOL * np.abs(exact) + ATOL), (k, np.abs(got - exact).max())
-    assert close.mean() > 0.99
+    assert np.all(np.abs(got - exact) <= RTOL * np.abs(exact) + 1e-5), (k, np.abs(got - exact).max())
 
 
 def test_reference_known_answers_sparse_weighted_jaccard():
@@ -146,11 +146,56 @@ def test_kernels_against_a_dense_restatement_on_random_features():
   assert np.abs(got - want).max() < 2e-6
 
 
-def test_negative_features_are_refused_not_silently_different():
+def _reference_loop(xi, xv, yi, yv):
+  """SparseWeightedJaccard's loop (hg2v_sample.py:257-275) on (sorted ids, fp32 values) rows."""
+  x, y = dict(zip(xi.tolist(), xv)), dict(zip(yi.tolist(), yv))
+  num = den = 0
+  for c in np.union1d(xi[xv != 0], yi[yv != 0]):
+    a, b = x.get(int(c), np.float32(0)), y.get(int(c), np.float32(0))
+    if a < b:
+      num += a
+      den += b
+    else:
+      num += b
+      den += a
+  return np.float32(0) if den == 0 else np.float32(num / den)
+
+
+def test_kernels_equal_the_reference_loop_bit_for_bit_negative_values_included():
+  """Rows and centroids against a restatement of the reference's loop in numpy fp32 scalars:
+  long rows (hundreds of non-zeros, where the summation order shows), groups of 1 .. 60 members,
+  an empty group, explicit zeros and negative feature values (the reference's formula has no sign
+  restriction: the smaller value goes to the numerator)."""
   from hypergraphembedding_b200 import _native
-  F = csr_matrix([[1.0, -2.0], [0.5, 1.0]], dtype=np.float32)
-  with pytest.raises(_native.NativeError):
-    _native.jaccard_rows(_native.default_context(), _native.FeatureCsr(F), [0], [1])
+  rng = np.random.default_rng(7)
+  F = sps.random(120, 900, density=0.35, random_state=3, format="csr", dtype=np.float32)
+  F.data[::17] *= -1
+  F.data[::29] = 0
+  F.sort_indices()
+  G = sps.random(40, 120, density=0.2, random_state=4, format="csr", dtype=np.float32)
+  G.data[:] = 1
+  G = sps.vstack([G, csr_matrix((1, 120), dtype=np.float32)]).tocsr()     # group 40 is empty
+  G.sort_indices()
+  ctx = _native.default_context()
+  feat, groups = _native.FeatureCsr(F), _native.CsrArrays(G)
+  row = lambda M, r: (M.indices[M.indptr[r]:M.indptr[r + 1]], M.data[M.indptr[r]:M.indptr[r + 1]])
+  pi, pj = rng.integers(0, 120, 300), rng.integers(0, 120, 300)
+  got = _native.jaccard_rows(ctx, feat, pi, pj)
+  want = np.asarray([_reference_loop(*row(F, a), *row(F, b)) for a, b in zip(pi, pj)], np.float32)
+  assert np.array_equal(got, want)
+  px, pg = rng.integers(0, 120, 300), np.concatenate([rng.integers(0, 40, 299), [40]])
+  got = _native.jaccard_centroid(ctx, feat, groups, feat, px, pg)
+  want = []
+  for a, grp in zip(px, pg):
+    members = G.indices[G.indptr[grp]:G.indptr[grp + 1]]
+    if len(members) == 0:
+      want.append(np.float32(0))
+      continue
+    centroid = F[members].sum(axis=0) / len(members)        # CentroidFromRows, hg2v_sample.py:293
+    assert centroid.dtype == np.float32
+    cols = centroid.nonzero()[1]
+    want.append(_reference_loop(*row(F, a), cols, np.asarray(centroid)[0, cols]))
+  assert np.array_equal(got, np.asarray(want, np.float32))
 
 
 def test_weighted_model_input_carries_the_jaccard_weights():
