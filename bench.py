@@ -420,13 +420,26 @@ def hg2v_train_extra(ctx, dimension=32, epochs=3):
     t = time.perf_counter()
     losses.append(model.fit_epoch(order, 256))
     secs.append(time.perf_counter() - t)
+  # the same records in batches of 4 096: one cluster per 256 samples, global barrier between phases
+  big = {}
+  for cap, key in ((0, "many_clusters"), (1, "one_cluster")):
+    ctx.set_trainer_clusters(cap)
+    model.fit_epoch(np.random.permutation(m), 4096)
+    t = time.perf_counter()
+    model.fit_epoch(np.random.permutation(m), 4096)
+    dt = time.perf_counter() - t
+    big[key] = {"clusters": model.last_clusters, "epoch_s": dt, "samples_per_s": m / dt,
+                "us_per_batch": 1e6 * dt / ((m + 4095) // 4096)}
+  ctx.reset_tuning()
   model.close()
   batches = (m + 255) // 256
   return {"workload": "UnweightedFloatModel on the %d HOBE records of snap_youtube_tiny, dimension %d, "
                       "num_neighbors 5, batch 256, Adagrad" % (m, dimension),
           "samples_per_s": m / min(secs), "epoch_s": min(secs), "us_per_batch": 1e6 * min(secs) / batches,
-          "batches_per_epoch": batches, "epoch_losses": losses,
-          "kernel": "k_hg2v_epoch: one launch per epoch, one 8-CTA cluster, 2 cluster barriers per batch"}
+          "batches_per_epoch": batches, "epoch_losses": losses, "batch_4096": big,
+          "kernel": "k_hg2v_epoch: one launch per epoch, one 8-CTA cluster per 256 samples of a batch, "
+                    "2 barriers per batch (hardware cluster barrier; + one global arrival per cluster "
+                    "when a batch spans several)"}
 
 
 def c1_end_to_end_extra(ctx, dimension=32):

@@ -53,6 +53,7 @@ SIGNATURES = {
     "hge_ctx_set_tuning": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hge_ctx_reset_tuning": (ctypes.c_int, [c_vp]),
     "hge_ctx_set_tile_mb": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    "hge_ctx_set_trainer_clusters": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "hge_ctx_launch_count": (ctypes.c_int64, [c_vp]),
     "hge_incidence_create": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp,
                                             c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
@@ -117,6 +118,7 @@ SIGNATURES = {
     "hge_hg2v_fit_epoch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_double)]),
     "hge_hg2v_get_weights": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
+    "hge_hg2v_last_clusters": (ctypes.c_int, [c_vp]),
     "hge_mt19937_random_raw": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp]),
     "hge_mt19937_interval": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_int64, c_vp]),
     "hge_spgemm_rows": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -240,6 +242,10 @@ class Context(object):
 
   def set_tile_mb(self, tile_mb, min_rows_mb=1024):
     check(self.lib.hge_ctx_set_tile_mb(self.handle, int(tile_mb), int(min_rows_mb)))
+
+  def set_trainer_clusters(self, max_clusters):
+    """Cap on the clusters of one hypergraph2vec training launch (0: what fits the device)."""
+    check(self.lib.hge_ctx_set_trainer_clusters(self.handle, int(max_clusters)))
 
   def reset_tuning(self):
     """Every schedule / kernel / tile knob back to the library's defaults."""

@@ -52,6 +52,7 @@ struct hge_ctx {
   int blocks_per_sm;
   int unit_cost;         // per-unit cost in steps when the stream is cut into pieces
   int p2p_slices;        // default number of slices the peer-memory exchange is pipelined in
+  int trainer_max_clusters;  // cap on the clusters of one hg2v training launch (0: what fits)
   int tile_mb;           // node-range tile of the single-GPU edge half in MB of rows (0 = off)
   int tile_min_mb;       // ... used when the node rows exceed this many MB
   int tile_force;        // min_rows_mb == 0 (tests): tile whatever the edge sizes are

@@ -76,6 +76,8 @@ static void set_default_tuning(hge_ctx* ctx) {
   // one slice; the pipeline is there for shapes whose exchange tail is longer.
   ctx->p2p_slices = 1;
   if (const char* env = getenv("HGE_P2P_SLICES")) ctx->p2p_slices = std::max(1, std::min(16, atoi(env)));
+  ctx->trainer_max_clusters = 0;
+  if (const char* env = getenv("HGE_TRAIN_MAX_CLUSTERS")) ctx->trainer_max_clusters = std::max(0, atoi(env));
   // random 128-byte gathers over 8 GB of rows run at a third of the rate they reach inside 1 GB;
   // the edge half over more than 512 MB of node rows is tiled by node range into L2-sized tiles
   // when the edges are large enough for that to pay (profiles/r1_tiled_edge_half.md)
@@ -197,6 +199,14 @@ int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb) {
   ctx->tile_mb = tile_mb;
   ctx->tile_min_mb = min_rows_mb;
   ctx->tile_force = min_rows_mb == 0;
+  return HGE_OK;
+}
+
+int hge_ctx_set_trainer_clusters(hge_ctx* ctx, int max_clusters) {
+  HGE_REQUIRE(ctx != nullptr, "hge_ctx_set_trainer_clusters: ctx is NULL");
+  HGE_REQUIRE(max_clusters >= 0 && max_clusters <= 64, "hge_ctx_set_trainer_clusters: %d not in [0, 64]",
+              max_clusters);
+  ctx->trainer_max_clusters = max_clusters;
   return HGE_OK;
 }
 

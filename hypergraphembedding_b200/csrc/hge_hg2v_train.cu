@@ -19,6 +19,12 @@
 // Tables, accumulators and gradients are read with ld.global.cg: other SMs rewrite them every
 // batch and L1 is not coherent.  A launch per batch would cost ~3 launches x 3 000 batches per
 // epoch on the 755 K-sample fixture run; here the per-batch cost is the two barriers.
+//
+// Batches of more than 256 samples: the same kernel is launched (cooperatively, so that every
+// block is resident) as ceil(batch / 256) clusters, up to what the device holds at once (16-18 on
+// B200), a sample per warp again, and the two per-batch barriers become cluster barrier ->
+// one arrival per cluster on a global counter -> cluster barrier.  The one-cluster launch keeps
+// the pure hardware barrier.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -41,6 +47,9 @@ struct hge_hg2v_model {
   double* d_loss = nullptr;
   int64_t M = 0;
   int32_t next_batch_id = 0;
+  unsigned int* grid_bar = nullptr;   // arrival counter of the inter-cluster batch barrier
+  int max_clusters = 0;               // co-resident clusters of k_hg2v_epoch (0: not asked yet)
+  int last_clusters = 0;              // clusters of the last epoch's launch
 };
 
 namespace {
@@ -61,6 +70,8 @@ struct TrainArgs {
   int64_t M;
   int dim, k, batch, activation, loss, batch_id0;
   float lr, eps;
+  int clusters;             // clusters of this launch
+  unsigned int* grid_bar;   // zero at launch
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -127,7 +138,31 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   __shared__ float s_g0[2][kMaxDim];   // gradient of the padding rows N[0], E[0] of this CTA
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  const int num_warps = kCluster * kWarpsPerCta;
+  const int num_warps = a.clusters * kCluster * kWarpsPerCta;
+  // batch barrier: everything every block of the launch wrote (gradient atomics, table updates)
+  // is visible to every block after it
+  unsigned int bar_target = 0;
+  auto batch_barrier = [&]() {
+    if (a.clusters == 1) {
+      // barrier.cluster arrive.release / wait.acquire: every CTA that touches the tables is in
+      // this cluster, so cluster scope orders the gradient atomics before the updates
+      cluster.sync();
+      return;
+    }
+    __threadfence();
+    cluster.sync();
+    bar_target += (unsigned int)a.clusters;
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.grid_bar, 1u);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.grid_bar) : "memory");
+      } while (seen < bar_target);
+      __threadfence();
+    }
+    cluster.sync();
+  };
   const int dim = a.dim, k = a.k, cols = 4 + 2 * k;
   for (int c = threadIdx.x; c < 2 * kMaxDim; c += kThreads) (&s_g0[0][0])[c] = 0.0f;
   __syncthreads();
@@ -269,9 +304,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       if (v != 0.0f) atomicAdd((t ? a.gE : a.gN) + cc, v);
       s_g0[t][cc] = 0.0f;
     }
-    // barrier.cluster arrive.release / wait.acquire: every CTA that touches the tables is in
-    // this cluster, so cluster scope orders the gradient atomics before the updates below
-    cluster.sync();
+    batch_barrier();
     if (b + 1 < num_batches)
       fetch(first + a.batch, (int)min((int64_t)a.batch, a.M - first - a.batch), warp, &my_next,
             &my_t_next);
@@ -329,7 +362,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         }
       }
     }
-    cluster.sync();
+    batch_barrier();
     my_first = my_next;
     my_t_first = my_t_next;
   }
@@ -366,6 +399,7 @@ int hge_hg2v_destroy(hge_hg2v_model* m) {
   hge_dev_free(ctx, m->target);
   hge_dev_free(ctx, m->order);
   hge_dev_free(ctx, m->d_loss);
+  hge_dev_free(ctx, m->grid_bar);
   delete m;
   return HGE_OK;
 }
@@ -402,6 +436,7 @@ int hge_hg2v_create(hge_ctx* ctx, int32_t node_rows, int32_t edge_rows, int dim,
   if (rc == HGE_OK) rc = hge_dev_alloc(ctx, &m->claimN, (size_t)node_rows);
   if (rc == HGE_OK) rc = hge_dev_alloc(ctx, &m->claimE, (size_t)edge_rows);
   if (rc == HGE_OK) rc = hge_dev_alloc(ctx, &m->d_loss, 1);
+  if (rc == HGE_OK) rc = hge_dev_alloc(ctx, &m->grid_bar, 1);
   if (rc == HGE_OK) {
     cudaError_t e = cudaMemsetAsync(m->accN, 0, nn * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->accE, 0, ne * 4, ctx->stream);
@@ -478,17 +513,62 @@ int hge_hg2v_fit_epoch(hge_hg2v_model* m, const int32_t* order, int batch_size, 
   a.lr = 0.01f; a.eps = 1e-7f;   // keras.optimizers.Adagrad defaults
   m->next_batch_id += (int32_t)num_batches;
   const int dpl = (m->dim + 31) / 32;
-  if (dpl <= 1) k_hg2v_epoch<1><<<kCluster, kThreads, 0, ctx->stream>>>(a);
-  else if (dpl <= 2) k_hg2v_epoch<2><<<kCluster, kThreads, 0, ctx->stream>>>(a);
-  else if (dpl <= 4) k_hg2v_epoch<4><<<kCluster, kThreads, 0, ctx->stream>>>(a);
-  else k_hg2v_epoch<8><<<kCluster, kThreads, 0, ctx->stream>>>(a);
-  HGE_CHECK_LAUNCH(ctx);
+  void (*kernel)(const TrainArgs) = dpl <= 1 ? k_hg2v_epoch<1> : dpl <= 2 ? k_hg2v_epoch<2>
+                                    : dpl <= 4 ? k_hg2v_epoch<4> : k_hg2v_epoch<8>;
+  // clusters that can be resident at once (they spin on each other): asked once per model
+  if (m->max_clusters == 0) {
+    cudaLaunchConfig_t probe = {};
+    probe.gridDim = dim3(kCluster * 32, 1, 1);
+    probe.blockDim = dim3(kThreads, 1, 1);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &probe) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 1;
+    }
+    m->max_clusters = n;
+  }
+  const int want = (int)std::min<int64_t>((std::min<int64_t>(batch_size, m->M) + kCluster * kWarpsPerCta - 1) /
+                                              (kCluster * kWarpsPerCta), m->max_clusters);
+  int clusters = std::max(1, std::min(want, ctx->trainer_max_clusters > 0 ? ctx->trainer_max_clusters : want));
+  a.grid_bar = m->grid_bar;
+  for (;;) {
+    a.clusters = clusters;
+    cudaError_t e = cudaSuccess;
+    if (clusters == 1) {
+      kernel<<<kCluster, kThreads, 0, ctx->stream>>>(a);
+      e = cudaGetLastError();
+    } else {
+      e = cudaMemsetAsync(m->grid_bar, 0, sizeof(unsigned int), ctx->stream);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kCluster * clusters, 1, 1);
+      cfg.blockDim = dim3(kThreads, 1, 1);
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;   // every block resident, or the launch fails
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kernel, a);
+    }
+    if (e == cudaSuccess) break;
+    cudaGetLastError();
+    if (clusters == 1) {
+      hge_set_error("hge_hg2v_fit_epoch: kernel launch failed: %s", cudaGetErrorString(e));
+      return HGE_ERR_CUDA;
+    }
+    clusters = clusters > 2 ? clusters / 2 : 1;   // fewer clusters fit: same result, more rounds per batch
+    m->max_clusters = clusters;
+  }
+  m->last_clusters = clusters;
+  ctx->launches++;
   double total = 0.0;
   HGE_CUDA(cudaMemcpyAsync(&total, m->d_loss, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   HGE_CUDA(cudaStreamSynchronize(ctx->stream));
   *epoch_loss = total / (double)m->M;
   return HGE_OK;
 }
+
+int hge_hg2v_last_clusters(const hge_hg2v_model* m) { return m ? m->last_clusters : 0; }
 
 int hge_hg2v_get_weights(hge_hg2v_model* m, float* node, float* edge, int mem) {
   HGE_REQUIRE(m && node && edge, "hge_hg2v_get_weights: NULL argument");

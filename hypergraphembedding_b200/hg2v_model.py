@@ -139,6 +139,11 @@ class Hg2vModel(object):
                   "hge_hg2v_fit_epoch")
     return loss.value
 
+  @property
+  def last_clusters(self):
+    """Thread-block clusters the last epoch ran on (one per 256 samples of a batch)."""
+    return int(self.ctx.lib.hge_hg2v_last_clusters(self.handle))
+
   def fit(self, x, y, batch_size=32, epochs=1, callbacks=None, verbose=1, shuffle=True):
     """keras Model.fit for this model family: per epoch the sample order is shuffled with the
     global numpy RNG (as keras.engine.training_arrays does), batches are consecutive slices of

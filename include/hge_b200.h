@@ -74,6 +74,9 @@ int hge_ctx_set_tuning(hge_ctx* ctx, int light_max_deg, int chunk, int blocks_pe
  * half on one GPU, 200 -> 159 ms per step on 8.  Results differ from the untiled half-sweep only
  * by fp32 summation order. */
 int hge_ctx_set_tile_mb(hge_ctx* ctx, int tile_mb, int min_rows_mb);
+/* hypergraph2vec training: at most this many 8-block clusters per epoch launch (0, the default:
+ * one per 256 samples of a batch, up to what the device holds at once). */
+int hge_ctx_set_trainer_clusters(hge_ctx* ctx, int max_clusters);
 /* Back to the defaults of hge_ctx_create for every knob above (tuning, kernel, tiles). */
 int hge_ctx_reset_tuning(hge_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
@@ -312,7 +315,9 @@ int hge_sample_neighbors(const int64_t* n2e_ptr, const int32_t* n2e_idx, const i
  * activation 0 = sigmoid (BooleanModel), 1 = relu (UnweightedFloatModel); loss 0 = Keras
  * kullback_leibler_divergence, 1 = mean_squared_error, summed over the three outputs; optimizer =
  * Keras Adagrad defaults (lr 0.01, epsilon 1e-7).  One call of hge_hg2v_fit_epoch is one epoch:
- * consecutive batches of `batch_size` samples taken in the given order, one kernel launch. */
+ * consecutive batches of `batch_size` samples taken in the given order, one kernel launch of one
+ * thread-block cluster per 256 samples of a batch (a sample per warp; several clusters are
+ * launched cooperatively and meet at a global barrier twice per batch). */
 typedef struct hge_hg2v_model hge_hg2v_model;
 int hge_hg2v_create(hge_ctx* ctx, int32_t node_rows, int32_t edge_rows, int dim, int num_neighbors,
                     int activation, int loss, const float* node_init, const float* edge_init,
@@ -328,6 +333,8 @@ int hge_hg2v_set_samples(hge_hg2v_model* m, const int32_t* features, const float
  * sample-weighted mean of the batch losses (what EarlyStopping(monitor="loss") watches). */
 int hge_hg2v_fit_epoch(hge_hg2v_model* m, const int32_t* order, int batch_size, int mem,
                        double* epoch_loss);
+/* Clusters the last hge_hg2v_fit_epoch launched (0 before the first). */
+int hge_hg2v_last_clusters(const hge_hg2v_model* m);
 int hge_hg2v_get_weights(hge_hg2v_model* m, float* node, float* edge, int mem);
 
 /* ---- hypergraph.proto wire format (host code; all pointers are host pointers) --------------

@@ -71,6 +71,44 @@ def test_epochs_match_the_float64_restatement(activation, loss, dim, k, batch):
   model.close()
 
 
+@pytest.mark.parametrize("activation,loss,dim,k,batch", [
+    ("relu", "mean_squared_error", 32, 3, 1024),
+    ("sigmoid", "kullback_leibler_divergence", 16, 5, 4096),
+    ("relu", "mean_squared_error", 70, 2, 5000),
+])
+def test_large_batches_on_several_clusters_match_the_restatement(activation, loss, dim, k, batch):
+  """Batches of more than 256 samples run on one cluster per 256 samples with a global barrier
+  between the phases: same result (up to the order of the gradient atomics) as the float64
+  restatement and as the same epochs forced onto one cluster."""
+  from hypergraphembedding_b200 import _native
+  feats, targets = _random_problem(50 + dim, nodes=3000, edges=1200, k=k, m=20000)
+  rng = np.random.default_rng(2)
+  n0 = rng.uniform(-0.7, 0.7, (3001, dim)).astype(np.float32)
+  e0 = rng.uniform(-0.7, 0.7, (1201, dim)).astype(np.float32)
+  m = len(feats[0])
+  orders = [np.random.default_rng(20 + e).permutation(m) for e in range(3)]
+  want_n, want_e, want_losses = ref.fit(n0, e0, feats, targets, k, activation,
+                                        "kld" if loss.startswith("kull") else "mse", batch, 3,
+                                        order=orders, min_delta=-1e9)
+  ctx = _native.default_context()
+  results = []
+  try:
+    for cap in (0, 1):
+      ctx.set_trainer_clusters(cap)
+      model = _model_with_tables(n0, e0, k, activation, loss)
+      model.set_samples(feats, targets)
+      losses = [model.fit_epoch(o, batch) for o in orders]
+      clusters = model.last_clusters
+      results.append((model.weights(), losses, clusters))
+      model.close()
+      assert np.allclose(losses, want_losses, rtol=2e-5, atol=1e-6), (cap, losses, want_losses)
+      got_n, got_e = results[-1][0]
+      assert np.abs(got_n - want_n).max() < 2e-4 and np.abs(got_e - want_e).max() < 2e-4, cap
+  finally:
+    ctx.reset_tuning()
+  assert results[0][2] > 1 and results[1][2] == 1, (results[0][2], results[1][2])
+
+
 def _model_with_tables(n0, e0, k, activation, loss):
   import ctypes
   from hypergraphembedding_b200 import _native
