@@ -1174,6 +1174,9 @@ def run_sharded(args, spec, world, rank, local_rank):
   # alone (the same kernel and shard shape as at N = 1)
   evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * sweeps + 1)]
   relax.ops.load(xn_init, xe_init)
+  arena = getattr(relax.ops, "arena", None) if relax.use_p2p else None
+  if arena is not None:
+    arena.set_timing(True)        # phase marks for this pass only, not in the timed region above
   for t in range(sweeps):
     evs[2 * t].record()
     if relax.use_p2p:
@@ -1185,6 +1188,15 @@ def run_sharded(args, spec, world, rank, local_rank):
   evs[2 * sweeps].record()
   torch.cuda.synchronize()
   sweep_ms = float(np.mean([evs[2 * t].elapsed_time(evs[2 * t + 2]) for t in range(sweeps)]))
+  phases = None
+  if arena is not None:
+    ms5, n_timed = arena.phase_ms()
+    arena.set_timing(False)
+    worst = torch.tensor(ms5, dtype=torch.float64, device="cuda")
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    phases = dict(zip(("node_half", "edge_gather_push", "barrier_a", "owner_reduce_all_gather",
+                       "barrier_b_minmax"), [float(v) for v in worst.tolist()]))
+    phases["note"] = "ms per sweep, max over ranks, CUDA events between the launches of %d sweeps" % n_timed
   peak, peak_src = hbm_peak()
   if relax.use_p2p:
     kernel = "fused sweep: k_sweep<8> node half + sliced edge gather with peer push, per-slice barrier + k_edge_reduce_push on a second stream, min/max barrier (rank 0)"
@@ -1258,7 +1270,7 @@ def run_sharded(args, spec, world, rank, local_rank):
         "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_launch,
-                     "ms_per_launch": launch_ms, "ms_per_sweep": sweep_ms},
+                     "ms_per_launch": launch_ms, "ms_per_sweep": sweep_ms, "sweep_phases_ms": phases},
         "cpu_baseline": None,
         "e2e": {"value": nnz_global * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
                 "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * world,

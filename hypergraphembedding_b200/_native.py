@@ -85,6 +85,8 @@ SIGNATURES = {
     "hge_p2p_export": (ctypes.c_int, [c_vp, c_vp]),
     "hge_p2p_open_peers": (ctypes.c_int, [c_vp, c_vp]),
     "hge_p2p_check": (ctypes.c_int, [c_vp]),
+    "hge_p2p_phase_ms": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "hge_p2p_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "hge_p2p_close_peers": (ctypes.c_int, [c_vp]),
     "hge_p2p_destroy": (ctypes.c_int, [c_vp]),
     "hge_algdist_attach_p2p": (ctypes.c_int, [c_vp, c_vp]),
@@ -708,6 +710,17 @@ class PeerArena(object):
 
   def check(self):
     check(self.ctx.lib.hge_p2p_check(self.handle), "hge_p2p_check")
+
+  def set_timing(self, on):
+    check(self.ctx.lib.hge_p2p_set_timing(self.handle, int(bool(on))), "hge_p2p_set_timing")
+
+  def phase_ms(self):
+    """(mean ms per sweep of [node half, gather + push, barrier A, reduce + all-gather, barrier B],
+    sweeps averaged over) since the last call; needs HGE_P2P_TIMING=1 when the arena was created."""
+    out = np.zeros(5, dtype=np.float64)
+    n = ctypes.c_int(0)
+    check(self.ctx.lib.hge_p2p_phase_ms(self.handle, ptr(out), ctypes.byref(n)), "hge_p2p_phase_ms")
+    return out.tolist(), int(n.value)
 
   def close_peers(self):
     if getattr(self, "handle", None):

@@ -154,12 +154,24 @@ struct hge_p2p {
   uint32_t** d_peer_flags = nullptr;
   uint32_t seq = 0;                          // barrier sequence number (same on every rank)
   bool peers_open = false;
-  // pipelined exchange: slice k's barrier + owner-side reduce run on `side` while slice k + 1 is
-  // gathered on the context's stream
+  // pipelined exchange: the owner-side work of the finished slices runs on `side` while the
+  // gather launch goes on with the next slices on the context's stream
   cudaStream_t side = nullptr;
-  cudaEvent_t gathered[16] = {nullptr};
   cudaEvent_t reduced = nullptr;
   std::vector<HgeHalfSchedule> slice_sched;  // the shard's edge half, one schedule per slice
+  // pipelined sweep (slices > 1): one dynamic gather launch over all slice schedules
+  // (hge_internal_edge_push_dynamic); the owner-side work follows slice by slice on `side`
+  void* d_dyn_src = nullptr;                 // device HgeSweepSrc[slices]
+  std::vector<char> h_dyn_src;               // what was uploaded last
+  int32_t* d_dyn_ctr = nullptr;              // [1 + slices]: next work item, finished pieces per slice
+  int dyn_pieces = 0;
+  int reserve_blocks = 0;                    // block slots the gather leaves to the owner-side kernels
+  uint32_t sweep_seq = 0;                    // sequence number of the per-slice arrival flags
+  cudaEvent_t node_done = nullptr;
+  // HGE_P2P_TIMING=1: events around the phases of every sweep (node half, gather + push,
+  // barrier A, owner reduce + all-gather, barrier B), read by hge_p2p_phase_ms
+  bool timing = false;
+  std::vector<cudaEvent_t> marks;            // 6 per recorded sweep
 };
 
 // (owner rank, row inside the owner's block) of an edge row -- shared by the kernels that push
@@ -197,4 +209,5 @@ struct hge_algdist {
 // internal: the sharded edge gather with the partial rows pushed to their owners (slice < 0: all
 // edge rows), and the per-slice schedules it runs over
 extern "C" int hge_internal_edge_push(hge_algdist* st, int sweep, int slice);
+extern "C" int hge_internal_edge_push_dynamic(hge_algdist* st, int sweep);
 extern "C" int hge_internal_slice_schedules(hge_algdist* st);

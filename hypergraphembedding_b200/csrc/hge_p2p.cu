@@ -13,10 +13,20 @@
 //                                                                   -> all-reduce(min / max)
 //
 // Pipelining.  The edge rows are cut into `slices` slices; inside a slice the ownership is split
-// over the ranks (HgeOwnerMap).  Slice k's barrier A and owner-side reduce run on a second,
-// higher-priority stream while slice k + 1 is being gathered on the context's stream, so the
-// serial tail of a sweep (one owner pass + `world` peer stores per row + two barriers: 0.10 of
-// 0.45 ms per sweep at 8 GPUs in round 1) shrinks to the last slice's.
+// over the ranks (HgeOwnerMap).  ONE gather launch walks all slices, slice-major, with warps
+// claiming (slice, piece) work items from a counter (HgeSweepDyn, hge_sweep.cuh); the warp that
+// finishes a slice's last piece raises that slice's arrival flag on every rank.  On a second,
+// higher-priority stream a one-block kernel waits for a slice's flags from all ranks and the
+// owner-side reduce of that slice follows -- in the block slots the gather launch leaves free
+// (reserve_blocks), while the gather goes on with the next slices, so that the serial tail of a
+// sweep (owner pass + `world` peer stores per row + two barriers: 0.115 of 0.42 ms per sweep at 4
+// and 8 GPUs) shrinks to the last slice's.  MEASURED (profiles/r2_multi_gpu.md): it does hide the
+// tail, but the gather launch pays more than the tail was worth -- 0.16 -> 0.25 ms at 8 GPUs
+// (fewer resident warps, the claim per piece, and the owner-side traffic now competes with the
+// gather for the same memory system) -- so `slices` defaults to 1 (no pipeline) and this path is
+// opt-in (HGE_P2P_SLICES, hge_p2p_create).  Round 2's first attempt, one gather launch per
+// slice, lost more: a launch fills every slot the previous one frees, so the owner-side kernels
+// only ran between the waves of the next gather.
 //
 // Each rank owns one cudaMalloc arena [edge rows | row of zeros | staging | bounds | flags |
 // error | local node rows] that the other ranks of the node map through CUDA IPC (the node rows
@@ -95,6 +105,22 @@ __global__ void k_exchange(int rank, int world, uint32_t seq, uint32_t* const* p
       mm_cur[i] = r;
     }
   }
+}
+
+// Waits until every rank has announced slice `slice` of the sweep numbered `seq` (the flags the
+// dynamic gather launch raises).  One block.
+__global__ void k_wait_slice(int world, uint32_t seq, const uint32_t* my_flags, int err_after_ns_hi, int* err) {
+  const int tid = threadIdx.x;
+  if (tid < world) {
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(my_flags + (size_t)tid * kFlagStride) - seq) < 0) {
+      if (global_ns() - t0 > kTimeoutNs) {
+        *err = 1;
+        break;
+      }
+    }
+  }
+  (void)err_after_ns_hi;
 }
 
 // Owner-side reduce of the staged partial rows + row update + push of the new row to all ranks.
@@ -208,7 +234,7 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, i
   HGE_REQUIRE(num_edges > 0 && ld > 0 && ld % 4 == 0, "hge_p2p_create: bad shape");
   HGE_REQUIRE(slices >= 0 && slices <= 16, "hge_p2p_create: slices %d not in [0, 16] (0 = default)", slices);
   if (slices == 0) slices = ctx->p2p_slices;
-  if (world == 1) slices = 1;
+  if (world == 1 && !getenv("HGE_P2P_SLICES_ONE_RANK")) slices = 1;   // one rank: nothing to overlap (the override is for profiling the gather launch)
   slices = std::max(1, std::min(slices, num_edges / std::max(1, 64 * world)));   // no sliver slices
   HGE_CUDA(cudaSetDevice(ctx->device));
   hge_p2p* p = new (std::nothrow) hge_p2p();
@@ -231,7 +257,7 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, i
   p->off_mmx = off;
   off = align_up(off + (size_t)2 * world * 2 * ld * 4, 256);
   p->off_flags = off;
-  off = align_up(off + (size_t)world * kFlagStride * 4, 256);
+  off = align_up(off + (size_t)(1 + 16) * world * kFlagStride * 4, 256);   // barrier + per-slice arrival flags
   p->off_err = off;
   off = align_up(off + 256, 256);
   // offsets above are the same on every rank (peers address them); the node rows differ in size
@@ -255,6 +281,10 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, i
     return HGE_ERR_CUDA;
   }
   p->peer_base[rank] = p->base;
+  if (const char* env = getenv("HGE_P2P_TIMING")) p->timing = atoi(env) != 0;
+  // block slots (of 256 threads) the pipelined gather leaves to the owner-side kernels
+  p->reserve_blocks = 32;
+  if (const char* env = getenv("HGE_P2P_RESERVE")) p->reserve_blocks = std::max(8, atoi(env));
   *out = p;
   return HGE_OK;
 }
@@ -333,10 +363,12 @@ int hge_p2p_destroy(hge_p2p* p) {
   if (p->side) {
     cudaStreamSynchronize(p->side);
     cudaStreamDestroy(p->side);
-    for (cudaEvent_t& e : p->gathered)
-      if (e) cudaEventDestroy(e);
     if (p->reduced) cudaEventDestroy(p->reduced);
   }
+  for (cudaEvent_t e : p->marks) cudaEventDestroy(e);
+  if (p->node_done) cudaEventDestroy(p->node_done);
+  if (p->d_dyn_src) cudaFree(p->d_dyn_src);
+  if (p->d_dyn_ctr) cudaFree(p->d_dyn_ctr);
   hge_dev_free(ctx, p->d_peer_stage);
   hge_dev_free(ctx, p->d_peer_ye);
   hge_dev_free(ctx, p->d_peer_mmx);
@@ -361,9 +393,8 @@ int hge_algdist_attach_p2p(hge_algdist* st, hge_p2p* p) {
     int lo = 0, hi = 0;
     HGE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     HGE_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi));
-    for (int k = 0; k < p->slices; ++k)
-      HGE_CUDA(cudaEventCreateWithFlags(&p->gathered[k], cudaEventDisableTiming));
     HGE_CUDA(cudaEventCreateWithFlags(&p->reduced, cudaEventDisableTiming));
+    HGE_CUDA(cudaEventCreateWithFlags(&p->node_done, cudaEventDisableTiming));
   }
   // a pooled arena may come back from a relaxation over another incidence of the same shape
   return hge_internal_slice_schedules(st);
@@ -416,26 +447,83 @@ int hge_algdist_sweep_p2p(hge_algdist* st, int sweep) {
   hge_p2p* p = st->p2p;
   hge_ctx* ctx = st->ctx;
   HGE_CUDA(cudaSetDevice(ctx->device));
+  // phase marks (HGE_P2P_TIMING): 6 events per sweep, up to 256 sweeps between two read-outs
+  const bool timed = p->timing && p->marks.size() < 6 * 256;
+  size_t mark0 = p->marks.size();
+  auto mark = [&]() {
+    if (!timed) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, ctx->stream);
+      p->marks.push_back(e);
+    }
+  };
+  mark();
   HGE_TRY(hge_algdist_node_half(st, sweep));
+  mark();
   if (p->slice_sched.empty()) {
     HGE_TRY(hge_internal_edge_push(st, sweep, -1));       // gather + reduce-scatter (peer stores)
+    mark();
     HGE_TRY(launch_exchange(st, -1, ctx->stream));        // barrier A
+    mark();
     HGE_TRY(launch_reduce_push(st, sweep, -1, ctx->stream));
+    mark();
   } else {
-    // slice k: gathered on the main stream; its barrier and reduce follow on the side stream
-    // while the main stream gathers slice k + 1.  Every rank issues the barriers in the same
-    // order (all of them on the side stream, then barrier B on the main stream after the join).
+    // one dynamic gather launch on the main stream; on the side stream, per slice: wait for the
+    // slice's arrival flags of all ranks, then the owner-side reduce + all-gather of the slice
+    p->sweep_seq += 1;
+    HGE_CUDA(cudaEventRecord(p->node_done, ctx->stream));
+    HGE_CUDA(cudaStreamWaitEvent(p->side, p->node_done, 0));
+    HGE_TRY(hge_internal_edge_push_dynamic(st, sweep));
+    uint32_t* my_flags = reinterpret_cast<uint32_t*>(p->base + p->off_flags);
     for (int k = 0; k < p->slices; ++k) {
-      HGE_TRY(hge_internal_edge_push(st, sweep, k));
-      HGE_CUDA(cudaEventRecord(p->gathered[k], ctx->stream));
-      HGE_CUDA(cudaStreamWaitEvent(p->side, p->gathered[k], 0));
-      HGE_TRY(launch_exchange(st, -1, p->side));
+      k_wait_slice<<<1, 32, 0, p->side>>>(p->world, p->sweep_seq,
+                                          my_flags + (size_t)(p->world + k * p->world) * kFlagStride, 0,
+                                          reinterpret_cast<int*>(p->base + p->off_err));
+      HGE_CHECK_LAUNCH(ctx);
       HGE_TRY(launch_reduce_push(st, sweep, k, p->side));
     }
+    mark();   // pipelined: the gather launch alone ...
     HGE_CUDA(cudaEventRecord(p->reduced, p->side));
     HGE_CUDA(cudaStreamWaitEvent(ctx->stream, p->reduced, 0));
+    mark();   // ... what is left of the owner-side work of the slices after it ...
+    mark();   // ... (nothing: slot kept so that the five phases line up with the unpipelined sweep)
   }
   HGE_TRY(launch_exchange(st, sweep, ctx->stream));       // barrier B + all-reduce(min / max)
+  mark();
+  if (timed && p->marks.size() != mark0 + 6) {            // an event could not be created: drop the sweep
+    while (p->marks.size() > mark0) {
+      cudaEventDestroy(p->marks.back());
+      p->marks.pop_back();
+    }
+  }
+  return HGE_OK;
+}
+
+int hge_p2p_set_timing(hge_p2p* p, int on) {
+  HGE_REQUIRE(p, "hge_p2p_set_timing: NULL argument");
+  p->timing = on != 0;
+  return HGE_OK;
+}
+
+// Mean milliseconds per sweep of the five phases recorded since the last call (HGE_P2P_TIMING=1):
+// node half, edge gather with the partial rows pushed to their owners, barrier A, owner-side
+// reduce + all-gather, barrier B with the min / max exchange.  *sweeps = sweeps averaged over.
+int hge_p2p_phase_ms(hge_p2p* p, double* out5, int* sweeps) {
+  HGE_REQUIRE(p && out5 && sweeps, "hge_p2p_phase_ms: NULL argument");
+  HGE_CUDA(cudaSetDevice(p->ctx->device));
+  HGE_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  const size_t n = p->marks.size() / 6;
+  for (int k = 0; k < 5; ++k) out5[k] = 0.0;
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 5; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, p->marks[6 * i + k], p->marks[6 * i + k + 1]);
+      out5[k] += ms / (double)n;
+    }
+  for (cudaEvent_t e : p->marks) cudaEventDestroy(e);
+  p->marks.clear();
+  *sweeps = (int)n;
   return HGE_OK;
 }
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ void kahan_add4(float4& s, float4& c, const float4& v
   y = v.w - c.w; t = s.w + y; c.w = (t - s.w) - y; s.w = t;
 }
 
-template <int LPR, int MODE>
+template <int LPR, int MODE, bool DYN>
 __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const HgeSweepArgs a) {
   constexpr int G = 32 / LPR;                      // lane groups (rows in flight) per warp
   constexpr int K = LPR >= 4 ? 1 : 4 / LPR;        // id registers per lane and step
@@ -186,11 +186,6 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
   float4 rmin = make_float4(kInf, kInf, kInf, kInf), rmax = make_float4(-kInf, -kInf, -kInf, -kInf);
 
   // ---- feeding ----------------------------------------------------------------------------
-  const int32_t* const sp = a.stream + g * 4 + (K == 1 ? (gl & 3) : gl);
-  auto load_ids = [&](uint32_t step, int (&r)[K]) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) r[k] = __ldcs(sp + (size_t)step * (4 * G) + LPR * k);
-  };
   auto issue_one = [&](quad& v, const int (&r)[K], const int j) {
 #if HGE_SWEEP_DEBUG & 2
     const int c = (r[0] + j) & 0xffff;
@@ -212,13 +207,6 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     }
 #endif
   };
-  // the id stream is read once, front to back: one lane per warp asks L2 for the line a few
-  // steps ahead, so the register ring above only has to cover an L2 hit
-  auto prefetch_ids = [&](uint32_t step) {
-    if (HGE_SWEEP_PREFETCH_STEPS > 0 && lane == 0)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stream + (size_t)(step + HGE_SWEEP_PREFETCH_STEPS) * (4 * G)));
-  };
-
   // ---- finishing ----------------------------------------------------------------------------
   // called by the lanes that own (row, c4); acc is the full gathered sum of the row
   auto finish_row = [&](int row, float degf, float invs, const float4& yown, const float4& acc) {
@@ -295,15 +283,29 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     return __ldcs(a.own + (size_t)row * ld4 + c4);
   };
 
-  const int pi = blockIdx.x * kWarps + warp;
-  const int32_t u0 = a.piece[pi], u1 = a.piece[pi + 1];
+  // ---- one piece of one schedule ----------------------------------------------------------------
+  auto run_piece = [&](const HgeSweepSrc& src, const int pi) {
+  // the schedule the piece belongs to: the launch's own, or (dynamic mode) a slice's
+  const int32_t* const stream0 = src.stream;
+  const int32_t* const sp = stream0 + g * 4 + (K == 1 ? (gl & 3) : gl);   // this lane's column of the id stream
+  auto load_ids = [&](uint32_t step, int (&r)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) r[k] = __ldcs(sp + (size_t)step * (4 * G) + LPR * k);
+  };
+  // the id stream is read once, front to back: one lane per warp asks L2 for the line a few
+  // steps ahead, so the register ring above only has to cover an L2 hit
+  auto prefetch_ids = [&](uint32_t step) {
+    if (HGE_SWEEP_PREFETCH_STEPS > 0 && lane == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(stream0 + (size_t)(step + HGE_SWEEP_PREFETCH_STEPS) * (4 * G)));
+  };
+  const int32_t u0 = src.piece[pi], u1 = src.piece[pi + 1];
 
   // ---- chunks of long rows: the G groups share the chunk ------------------------------------
-  for (int32_t u = u0; u < min(u1, a.n_chunks); ++u) {
-    const int2 ch = a.chunks[u];
-    const HgeHeavyRow hr = a.hrows[ch.x];
-    const uint32_t pos = a.uoff[u];
-    const uint32_t total = a.uoff[u + 1] - pos;
+  for (int32_t u = u0; u < min(u1, src.n_chunks); ++u) {
+    const int2 ch = src.chunks[u];
+    const HgeHeavyRow hr = src.hrows[ch.x];
+    const uint32_t pos = src.uoff[u];
+    const uint32_t total = src.uoff[u + 1] - pos;
     int r[D][K];
 #pragma unroll
     for (int d = 0; d < D; ++d) load_ids(pos + d, r[d]);
@@ -345,11 +347,11 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
       }
       continue;
     }
-    if (g == 0 && active) __stcg(a.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
+    if (g == 0 && active) __stcg(src.partials + (size_t)(hr.partial_base + ch.y) * ld4 + c4, acc);
     __threadfence();
     __syncwarp();
     int prev = 0;
-    if (lane == 0) prev = atomicAdd(a.counters + (size_t)slab * a.n_hrows + ch.x, 1);
+    if (lane == 0) prev = atomicAdd(src.counters + (size_t)slab * src.n_hrows + ch.x, 1);
     prev = __shfl_sync(kFull, prev, 0);
     if (prev != hr.nchunks - 1) continue;
     __threadfence();
@@ -357,21 +359,21 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     if (kOwn && g == 0 && active) yown = load_own(hr.row);
     float4 tot = hge_f4_zero(), tcomp = hge_f4_zero();
     for (int k = g; k < hr.nchunks; k += G)
-      if (active) kahan_add4(tot, tcomp, __ldcg(a.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
+      if (active) kahan_add4(tot, tcomp, __ldcg(src.partials + (size_t)(hr.partial_base + k) * ld4 + c4));
     tot = make_float4(tot.x - tcomp.x, tot.y - tcomp.y, tot.z - tcomp.z, tot.w - tcomp.w);
     reduce_groups(tot);
     if (g == 0 && active) finish_row(hr.row, (float)hr.deg, hr.invs, yown, tot);
-    if (lane == 0) a.counters[(size_t)slab * a.n_hrows + ch.x] = 0;   // ready for the next launch
+    if (lane == 0) src.counters[(size_t)slab * src.n_hrows + ch.x] = 0;   // ready for the next launch
   }
 
   // ---- groups of G short rows: group g gathers row g ------------------------------------------
-  const int32_t q0 = max(u0, a.n_chunks);
+  const int32_t q0 = max(u0, src.n_chunks);
   if (q0 < u1) {
-    const uint32_t pos = a.uoff[q0];
-    const uint32_t total = a.uoff[u1] - pos;
+    const uint32_t pos = src.uoff[q0];
+    const uint32_t total = src.uoff[u1] - pos;
     // descriptor ring: lane l copies item (32 blk + l) of the piece into half (blk & 1)
     int4(*ring)[32] = s_items[warp];
-    const int4* const ibase = a.items + (size_t)(q0 - a.n_chunks) * G + lane;
+    const int4* const ibase = src.items + (size_t)(q0 - src.n_chunks) * G + lane;
     cp_async16(&ring[0][lane], ibase);
     cp_async_commit();
     cp_async16(&ring[1][lane], ibase + 32);
@@ -462,6 +464,43 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
     }
     cp_async_wait<0>();
   }
+  };   // run_piece
+
+  if (!DYN) {
+    run_piece(a.src, blockIdx.x * kWarps + warp);
+  } else {
+    const int32_t total_items = a.dyn.slices * a.dyn.pieces;
+    for (;;) {
+      int32_t w = 0;
+      if (lane == 0) w = atomicAdd(a.dyn.next, 1);
+      w = __shfl_sync(kFull, w, 0);
+      if (w >= total_items) break;
+      const int32_t slice = w / a.dyn.pieces;
+      const HgeSweepSrc& src = a.dyn.src[slice];
+      run_piece(src, w - slice * a.dyn.pieces);
+      // This warp's partial rows are on their way to their owners.  The count is a release at
+      // GPU scope (orders the lanes' stores, made visible to the counting lane by the warp
+      // barrier, before the increment); the warp that takes the last count acquires it, fences at
+      // system scope once and raises the flag on every rank.  One system-scope fence per piece
+      // instead (MEMBAR.SYS, ~7 us each) was 15 % of the launch.
+      __syncwarp();
+      if (lane == 0) {
+        int32_t before;
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(before) : "l"(a.dyn.done + slice) : "memory");
+        if (before == a.dyn.pieces - 1) {
+          // last piece of the slice on this rank: every rank may reduce its rows of the slice
+          // as soon as it has seen this from all ranks
+          a.dyn.done[slice] = 0;
+          __threadfence_system();
+          for (int p = 0; p < a.dyn.world; ++p) {
+            uint32_t* flag = a.dyn.peer_flags[p] +
+                             (size_t)(a.dyn.flag0 + slice * a.dyn.world + a.dyn.rank) * a.dyn.flag_stride;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.dyn.seq) : "memory");
+          }
+        }
+      }
+    }
+  }
 
   // ---- per-column min / max of the rows this block produced -------------------------------------
   if (kOwn) {
@@ -509,11 +548,14 @@ __global__ void __launch_bounds__(kBlock, HGE_SWEEP_MIN_BLOCKS) k_sweep(const Hg
 template <int LPR>
 int launch_mode(const HgeSweepArgs& a, int mode, dim3 grid, cudaStream_t stream) {
   switch (mode) {
-    case kSweepNode: k_sweep<LPR, kSweepNode><<<grid, kBlock, 0, stream>>>(a); break;
-    case kSweepEdge: k_sweep<LPR, kSweepEdge><<<grid, kBlock, 0, stream>>>(a); break;
-    case kSweepRaw: k_sweep<LPR, kSweepRaw><<<grid, kBlock, 0, stream>>>(a); break;
-    case kSweepRawAdd: k_sweep<LPR, kSweepRawAdd><<<grid, kBlock, 0, stream>>>(a); break;
-    default: k_sweep<LPR, kSweepPush><<<grid, kBlock, 0, stream>>>(a); break;
+    case kSweepNode: k_sweep<LPR, kSweepNode, false><<<grid, kBlock, 0, stream>>>(a); break;
+    case kSweepEdge: k_sweep<LPR, kSweepEdge, false><<<grid, kBlock, 0, stream>>>(a); break;
+    case kSweepRaw: k_sweep<LPR, kSweepRaw, false><<<grid, kBlock, 0, stream>>>(a); break;
+    case kSweepRawAdd: k_sweep<LPR, kSweepRawAdd, false><<<grid, kBlock, 0, stream>>>(a); break;
+    default:
+      if (a.dyn.src) k_sweep<LPR, kSweepPush, true><<<grid, kBlock, 0, stream>>>(a);
+      else k_sweep<LPR, kSweepPush, false><<<grid, kBlock, 0, stream>>>(a);
+      break;
   }
   return HGE_OK;
 }
@@ -521,7 +563,7 @@ int launch_mode(const HgeSweepArgs& a, int mode, dim3 grid, cudaStream_t stream)
 template <int LPR>
 int resident_blocks(int* out) {
   int per_sm = 0;
-  HGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<LPR, kSweepNode>, kBlock, 0));
+  HGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<LPR, kSweepNode, false>, kBlock, 0));
   *out = per_sm < 1 ? 1 : per_sm;
   return HGE_OK;
 }

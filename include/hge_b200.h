@@ -176,6 +176,13 @@ int hge_p2p_create(hge_ctx* ctx, int rank, int world, int32_t num_local_nodes, i
 int hge_p2p_export(hge_p2p* p, void* handle64);
 int hge_p2p_open_peers(hge_p2p* p, const void* handles /* world x 64 bytes */);
 int hge_p2p_check(hge_p2p* p);
+/* Phase timing of the peer-memory sweep (off by default; hge_p2p_set_timing or HGE_P2P_TIMING=1
+ * in the environment at hge_p2p_create): CUDA events around the five phases of every sweep.
+ * hge_p2p_phase_ms returns the mean ms per sweep of each since the last call -- node half, edge
+ * gather + push, barrier A, owner reduce + all-gather, barrier B + min/max -- and the number of
+ * sweeps averaged over (0: nothing recorded). */
+int hge_p2p_set_timing(hge_p2p* p, int on);
+int hge_p2p_phase_ms(hge_p2p* p, double* out5, int* sweeps);
 int hge_p2p_close_peers(hge_p2p* p);   /* all ranks, then a host barrier, then destroy */
 int hge_p2p_destroy(hge_p2p* p);
 int hge_algdist_attach_p2p(hge_algdist* st, hge_p2p* p);
