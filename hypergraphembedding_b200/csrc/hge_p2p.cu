@@ -1,7 +1,7 @@
 // Peer-memory exchange for the row-partitioned relaxation: the collectives of the sharded edge
 // half are done by the kernels themselves over NVLink, with no NCCL kernel competing for SMs.
 //
-//   gather (k_half_sweep, push mode)   every rank stores the raw partial sum of edge e straight
+//   gather (k_sweep, push mode)        every rank stores the raw partial sum of edge e straight
 //                                      into the staging block of e's OWNER  -> reduce-scatter
 //   barrier A                          flags in peer memory
 //   k_edge_reduce_push                 the owner adds the `world` staged rows in rank order
@@ -513,9 +513,13 @@ int hge_p2p_phase_ms(hge_p2p* p, double* out5, int* sweeps) {
   HGE_REQUIRE(p && out5 && sweeps, "hge_p2p_phase_ms: NULL argument");
   HGE_CUDA(cudaSetDevice(p->ctx->device));
   HGE_CUDA(cudaStreamSynchronize(p->ctx->stream));
-  const size_t n = p->marks.size() / 6;
+  // the first recorded sweep waits for the slowest rank to arrive at all (tens of ms of skew that
+  // belong to whatever ran before): it is left out when there are others
+  const size_t total = p->marks.size() / 6;
+  const size_t first = total > 1 ? 1 : 0;
+  const size_t n = total - first;
   for (int k = 0; k < 5; ++k) out5[k] = 0.0;
-  for (size_t i = 0; i < n; ++i)
+  for (size_t i = first; i < total; ++i)
     for (int k = 0; k < 5; ++k) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, p->marks[6 * i + k], p->marks[6 * i + k + 1]);

@@ -533,7 +533,12 @@ int sampler_threads_for(int kind, int64_t num_rows) {
     if (kind == 0 || num_rows < 512) return 1;   // small jobs: thread start-up costs more
     // measured (16-core host, 3.5e8 candidates): 2.42 s inline, 1.11 s with 2 to 12 workers --
     // from two workers on the draw loop (3.1 ns per candidate) is all that is left
-    n = (int)std::min<unsigned>(4u, std::max(1u, std::thread::hardware_concurrency()));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    n = (int)std::min(4u, hw);
+    // three-factor rows (the node-edge pairs of HOBE / FOBE: candidates two hops away) cost far
+    // more to build than to draw from; on the 100 000-node HOBE case the builders scale to 8+
+    // workers (3.9 s with 1, 0.9 s with 4 on an 8-core host)
+    if (kind == 2) n = (int)std::min(16u, std::max(4u, hw / 2));
   }
   return std::max(1, n);
 }
