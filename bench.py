@@ -389,6 +389,53 @@ def hobe_scale_extra(ctx):
           "unit": "weighted samples/s (CSR + dense vectors in, columnar records out)"}
 
 
+def fobe_scale_extra(ctx):
+  """FOBE (BooleanSamples, hg2v_sample.py:125-242) on the config-4 family inside the default line:
+  the 100 000-node member against the committed digest of the scipy / numpy oracle
+  (tests/golden/boolean_c4.npz: 11.0 M records, index / neighbour columns and RNG state by
+  SHA-256), then the 1 000 000-node member for throughput (the 10 M-node configs[3] itself is
+  `--workload c4`: ~1e9 records).  Host work: FOBE probabilities are all 1."""
+  import hashlib
+  from hypergraphembedding_b200 import synthetic
+  from hypergraphembedding_b200.hg2v_sample import BooleanSamplesCsr
+  g = np.load(os.path.join(ROOT, "tests", "golden", "boolean_c4.npz"))
+
+  def sha(arrays, keys):
+    h = hashlib.sha256()
+    for k in keys:
+      h.update(np.ascontiguousarray(arrays[k], dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+  A = synthetic.zipf_hypergraph(100000, 50000, seed=int(g["graph_seed"]))
+  np.random.seed(int(g["seed"]))
+  t = time.perf_counter()
+  out = BooleanSamplesCsr(A, int(g["k"]), int(g["num_samples"]))
+  small_s = time.perf_counter() - t
+  arrays = out.arrays()
+  state = np.random.get_state()
+  exact = bool(len(out) == int(g["standalone_count"]) and
+               sha(arrays, ("left_node", "left_edge", "right_node", "right_edge")) == str(g["standalone_index_sha"]) and
+               sha(arrays, ("neigh_node", "neigh_edge")) == str(g["standalone_neigh_sha"]) and
+               int(state[2]) == int(g["standalone_rng_pos"]) and
+               hashlib.sha256(state[1].tobytes()).hexdigest() == str(g["standalone_rng_key_sha"]))
+  del out, arrays
+  A = synthetic.zipf_hypergraph(1000000, 500000, seed=int(g["graph_seed"]))
+  np.random.seed(int(g["seed"]))
+  t = time.perf_counter()
+  out = BooleanSamplesCsr(A, int(g["k"]), int(g["num_samples"]))
+  big_s = time.perf_counter() - t
+  records = len(out)
+  del out
+  return {"workload": "config-4 family (Zipf degrees), num_neighbors %d, num_samples %d" % (int(g["k"]),
+                                                                                           int(g["num_samples"])),
+          "nodes_100k": {"records": int(g["standalone_count"]), "seconds": small_s,
+                         "samples_per_s": int(g["standalone_count"]) / small_s,
+                         "bit_exact_vs_oracle_digest": exact},
+          "nodes_1m": {"incidences": int(A.nnz), "records": records, "seconds": big_s,
+                       "samples_per_s": records / big_s},
+          "unit": "samples/s (CSR in, columnar records out; host RNG replay)"}
+
+
 def hg2v_train_extra(ctx, dimension=32, epochs=3):
   """The consumer of the HOBE sample columns: UnweightedFloatModel (hg2v_model.py:129-203) trained
   on the 755 267 configs[0] records with the reference's fit settings (batch 256, Adagrad;
@@ -508,6 +555,29 @@ def pair_weighting_extra(ctx, num_pairs=100000000):
   ev[3].record()
   torch.cuda.synchronize()
   relax_ms, pair_ms = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+  # parity at full size: the L2 distances of every 997th pair against numpy f64 on the same
+  # vectors (|d - d_ref| <= 1e-5 d_ref + 1e-6 sqrt(R)), and the transform
+  # 1 - (d - min) / (max - min) of ALL pairs recomputed from those distances with the extrema
+  # taken over all 100 M of them (hg2v_weighting.py:94-95, 301-333)
+  d_raw = _native.pair_l2(ctx, xn, xe, ia, ib)
+  w_all = d_raw.clone()
+  _native.scale_transform(ctx, w_all, 0.0)
+  sel = torch.arange(0, num_pairs, 997, device="cuda")
+  hn, he = xn.cpu().numpy().astype(np.float64), xe.cpu().numpy().astype(np.float64)
+  sa, sb = ia[sel].cpu().numpy(), ib[sel].cpu().numpy()
+  d_ref = np.sqrt(((hn[sa] - he[sb])**2).sum(axis=1))
+  d_got = d_raw[sel].cpu().numpy().astype(np.float64)
+  dist_ratio = float((np.abs(d_got - d_ref) / (1e-5 * d_ref + 1e-6 * np.sqrt(R))).max())
+  lo, hi = float(d_raw.min()), float(d_raw.max())
+  w_ref = 1.0 - (d_got - lo) / (hi - lo)
+  w_got = w_all[sel].cpu().numpy().astype(np.float64)
+  weight_ratio = float((np.abs(w_got - w_ref) / (1e-5 * np.abs(w_ref) + 1e-6)).max())
+  parity = {"pairs_checked": int(len(sel)), "max_dist_err_over_bound": dist_ratio,
+            "max_weight_err_over_bound": weight_ratio,
+            "weights_in_unit_interval": bool(float(w_all.min()) == 0.0 and float(w_all.max()) == 1.0),
+            "ok": bool(dist_ratio <= 1.0 and weight_ratio <= 1.0),
+            "against": "numpy f64 on the same vectors, every 997th of the %d pairs" % num_pairs}
+  del d_raw, w_all
   inc.close()
   bytes_pair = 8 * R + 12
   peak, _ = hbm_peak()
@@ -518,7 +588,7 @@ def pair_weighting_extra(ctx, num_pairs=100000000):
           "frac_of_measured_hbm_peak": num_pairs * bytes_pair / (pair_ms * 1e-3) / 1e9 / peak,
           "relaxation_ms_20_sweeps": relax_ms,
           "relaxation_nnz_R_iters_per_s": A.nnz * R * sweeps / (relax_ms * 1e-3),
-          "generate_s": gen_s}
+          "parity": parity, "generate_s": gen_s}
 
 
 def run_fobe(args, spec):
@@ -726,7 +796,8 @@ def run_ours(args, spec):
     inc.close()
     del a_ptr, a_idx, b_ptr, b_idx, xn, xe, xn_init, xe_init
     torch.cuda.empty_cache()
-    for key, fn in (("hobe", hobe_extra), ("hobe_scale", hobe_scale_extra), ("hg2v_train", hg2v_train_extra),
+    for key, fn in (("hobe", hobe_extra), ("hobe_scale", hobe_scale_extra), ("fobe_scale", fobe_scale_extra),
+                    ("hg2v_train", hg2v_train_extra),
                     ("c1_end_to_end", c1_end_to_end_extra),
                     ("pair_weighting", pair_weighting_extra),
                     ("c5", lambda c: c5_extra(args, 1, 0, local_rank, c))):
