@@ -756,10 +756,9 @@ def run_ours(args, spec):
   def step_host():
     # the vectors are relaxed in place; the next step starts from this step's output, which is
     # again a valid input in [0, 1] (no host-to-host reset copy inside the timed region)
-    # one orientation is uploaded; the library transposes it on the device
-    inc_h = _native.Incidence(ctx, N, E, h_aptr.numpy(), h_aidx.numpy())
-    _native.algdist_run(ctx, inc_h, h_xn.numpy(), h_xe.numpy(), sweeps)
-    inc_h.close()
+    # one orientation is uploaded; the library transposes it on the device.  One call of the
+    # C ABI (hge_algdist_run_csr: what EmbedAlgebraicDistance makes per hypergraph)
+    _native.algdist_run_csr(ctx, N, E, h_aptr.numpy(), h_aidx.numpy(), h_xn.numpy(), h_xe.numpy(), sweeps)
 
   e2e_steps = max(1, min(args.steps, 5))
   h_xn.copy_(h_xn0)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "hge_incidence_nnz": (ctypes.c_int64, [c_vp]),
     "hge_algdist_run": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, c_vp]),
+    "hge_algdist_run_csr": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "hge_column_rescale": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int,
                                           ctypes.c_int]),
     "hge_algdist_create": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int,
@@ -393,6 +395,28 @@ def algdist_run(ctx, inc, xn, xe, iterations, lohi=None):
     assert lohi.dtype == np.float32 and lohi.shape == (iterations, 2, R)
   check(ctx.lib.hge_algdist_run(ctx.handle, inc.handle, ptr(xn), ptr(xe), R, int(iterations),
                                 MEM_DEVICE if device else MEM_HOST, ptr(lohi)), "hge_algdist_run")
+  return xn, xe
+
+
+def algdist_run_csr(ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, xn, xe, iterations, e2n_ptr=None,
+                    e2n_idx=None, lohi=None):
+  """hge_algdist_run_csr: incidence set-up + relaxation in one call on host (numpy) or device
+  (torch CUDA) arrays, in place; int64 row pointers, int32 sorted column ids."""
+  device = is_device(xn)
+  assert device == is_device(xe) == is_device(n2e_idx)
+  assert (e2n_ptr is None) == (e2n_idx is None)
+  R = int(xn.shape[1])
+  assert tuple(xn.shape) == (num_nodes, R) and tuple(xe.shape) == (num_edges, R)
+  if not device:
+    assert xn.dtype == np.float32 and xe.dtype == np.float32
+    n2e_ptr, n2e_idx = _as_i64(n2e_ptr), _as_i32(n2e_idx)
+    if e2n_ptr is not None:
+      e2n_ptr, e2n_idx = _as_i64(e2n_ptr), _as_i32(e2n_idx)
+  if lohi is not None:
+    assert lohi.dtype == np.float32 and lohi.shape == (iterations, 2, R)
+  check(ctx.lib.hge_algdist_run_csr(ctx.handle, int(num_nodes), int(num_edges), ptr(n2e_ptr), ptr(n2e_idx),
+                                    ptr(e2n_ptr), ptr(e2n_idx), ptr(xn), ptr(xe), R, int(iterations),
+                                    MEM_DEVICE if device else MEM_HOST, ptr(lohi)), "hge_algdist_run_csr")
   return xn, xe
 
 

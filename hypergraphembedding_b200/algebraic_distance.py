@@ -27,6 +27,16 @@ def relax(incidence, node_vectors, edge_vectors, iterations, ctx=None, lohi=None
   return _native.algdist_run(ctx, incidence, node_vectors, edge_vectors, iterations, lohi=lohi)
 
 
+def relax_csr(n2e_csr, node_vectors, edge_vectors, iterations, ctx=None, lohi=None):
+  """Incidence set-up + relaxation in one library call (hge_algdist_run_csr), in place on fp32
+  numpy arrays: what a caller that relaxes one hypergraph once wants -- the vectors' upload
+  overlaps the set-up kernels.  The edge -> node orientation is built on the device."""
+  ctx = ctx or _native.default_context()
+  a_ptr, a_idx = csr_arrays(n2e_csr)
+  return _native.algdist_run_csr(ctx, n2e_csr.shape[0], n2e_csr.shape[1], a_ptr, a_idx, node_vectors,
+                                 edge_vectors, iterations, lohi=lohi)
+
+
 def make_incidence(n2e_csr, e2n_csr=None, ctx=None):
   """Uploads a scipy N x E incidence matrix (and its E x N counterpart, default: transpose)."""
   ctx = ctx or _native.default_context()
@@ -100,14 +110,10 @@ def EmbedAlgebraicDistance(hypergraph,
   node_embeddings = np.random.random((num_nodes, dimension)).astype(np.float32)
   edge_embeddings = np.random.random((num_edges, dimension)).astype(np.float32)
 
-  log.info("Uploading node-edge incidence")
-  incidence = _native.Incidence(_native.default_context(), num_nodes, num_edges, a_ptr, a_idx,
-                                b_ptr, b_idx)
-  try:
-    log.info("Performing iterations of Algebraic Distance Calculations")
-    relax(incidence, node_embeddings, edge_embeddings, iterations)
-  finally:
-    incidence.close()
+  log.info("Performing iterations of Algebraic Distance Calculations")
+  # incidence upload, schedules and the sweeps in one library call (hge_algdist_run_csr)
+  _native.algdist_run_csr(_native.default_context(), num_nodes, num_edges, a_ptr, a_idx, node_embeddings,
+                          edge_embeddings, iterations, e2n_ptr=b_ptr, e2n_idx=b_idx)
 
   # arrays -> proto through the wire format: no per-row packing loop (algebraic_distance.py:169-174)
   embedding = HypergraphEmbedding()

@@ -470,7 +470,7 @@ static int incidence_finish(hge_incidence* inc);
 static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges,
                                  const int64_t* n2e_ptr, const int32_t* n2e_idx,
                                  const int64_t* e2n_ptr, const int32_t* e2n_idx, bool sharded,
-                                 int num_slices, int mem, hge_incidence** out) {
+                                 int num_slices, int mem, hge_incidence** out, bool defer_finish = false) {
   const char* fn = sharded ? "hge_incidence_create_sharded" : "hge_incidence_create";
   HGE_REQUIRE(ctx && out, "%s: NULL ctx / out", fn);
   *out = nullptr;
@@ -598,7 +598,7 @@ static int incidence_create_impl(hge_ctx* ctx, int32_t num_nodes, int32_t num_ed
   // edge weight sums: sum over (local) members n of 1 / deg(n); node degrees are complete
   rc = compute_wsum(ctx, num_edges, inc->e2n_ptr, inc->e2n_idx, nh.deg, &inc->edge_wsum);
   if (rc != HGE_OK) return fail(rc);
-  if (!sharded) {
+  if (!sharded && !defer_finish) {
     rc = incidence_finish(inc);
     if (rc != HGE_OK) return fail(rc);
   }
@@ -854,7 +854,21 @@ int hge_algdist_destroy(hge_algdist* st) {
 
 int hge_algdist_ld(const hge_algdist* st) { return st ? st->ld : 0; }
 
-int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem) {
+// Starts the upload of host vectors into the context's staging block on the copy stream (it runs
+// next to whatever is queued on the main stream) and records copy_done.
+static int stage_vectors(hge_ctx* ctx, int64_t N, int64_t E, int R, const float* xn, const float* xe) {
+  float* stage = nullptr;
+  HGE_TRY(hge_ctx_stage(ctx, (size_t)(N + E) * R, &stage));
+  HGE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_idle, 0));
+  HGE_CUDA(cudaMemcpyAsync(stage, xn, (size_t)N * R * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+  HGE_CUDA(cudaMemcpyAsync(stage + (size_t)N * R, xe, (size_t)E * R * 4, cudaMemcpyHostToDevice,
+                           ctx->copy_stream));
+  HGE_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  return HGE_OK;
+}
+
+// prestaged: stage_vectors has been called for these vectors already
+static int algdist_load_impl(hge_algdist* st, const float* xn, const float* xe, int mem, bool prestaged) {
   HGE_REQUIRE(st && xn && xe, "hge_algdist_load: NULL argument");
   hge_ctx* ctx = st->ctx;
   hge_incidence* inc = st->inc;
@@ -864,19 +878,10 @@ int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem)
   if (mem == HGE_MEM_HOST) {
     // upload on the copy stream: it starts now, next to whatever set-up work is still queued
     // on the main stream, which only waits for it right before k_load_rows
-    float* stage = nullptr;
-    HGE_TRY(hge_ctx_stage(ctx, (size_t)(inc->N + (int64_t)inc->E) * st->R, &stage));
-    float* sn = stage;
-    float* se = stage + (size_t)inc->N * st->R;
-    HGE_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_idle, 0));
-    HGE_CUDA(cudaMemcpyAsync(sn, xn, (size_t)inc->N * st->R * 4, cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-    HGE_CUDA(cudaMemcpyAsync(se, xe, (size_t)inc->E * st->R * 4, cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-    HGE_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    if (!prestaged) HGE_TRY(stage_vectors(ctx, inc->N, inc->E, st->R, xn, xe));
     HGE_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
-    dn = sn;
-    de = se;
+    dn = ctx->stage;
+    de = ctx->stage + (size_t)inc->N * st->R;
   }
   k_fill_minmax<<<grid_1d(ctx, (int64_t)std::max(1, st->max_iters) * 2 * st->ld, kBlock), kBlock, 0,
                   ctx->stream>>>(st->mm, std::max(1, st->max_iters), st->ld);
@@ -889,6 +894,10 @@ int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem)
   HGE_CHECK_LAUNCH(ctx);
   if (mem == HGE_MEM_HOST) HGE_CUDA(cudaEventRecord(ctx->stage_idle, ctx->stream));
   return HGE_OK;
+}
+
+int hge_algdist_load(hge_algdist* st, const float* xn, const float* xe, int mem) {
+  return algdist_load_impl(st, xn, xe, mem, false);
 }
 
 int hge_algdist_node_half(hge_algdist* st, int sweep) {
@@ -1143,11 +1152,8 @@ int hge_column_rescale(hge_ctx* ctx, float* xn, int64_t num_nodes, float* xe, in
   return HGE_OK;
 }
 
-int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R, int iterations,
-                    int mem, float* lohi) {
-  HGE_REQUIRE(ctx && inc && xn && xe, "hge_algdist_run: NULL argument");
-  HGE_REQUIRE(iterations >= 0, "hge_algdist_run: negative iteration count");
-  if (iterations == 0) return HGE_OK;  // the initial vectors are the result
+static int algdist_run_impl(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R, int iterations,
+                            int mem, float* lohi, bool prestaged) {
   // the workspace (Y rows, min/max slots, partial sums) is kept with the incidence and re-used
   hge_algdist* st = inc->cached;
   if (!st || st->R != R || st->max_iters < iterations || st->ctx != ctx) {
@@ -1156,7 +1162,7 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
     HGE_TRY(hge_algdist_create(ctx, inc, R, iterations, &st));
     inc->cached = st;
   }
-  int rc = hge_algdist_load(st, xn, xe, mem);
+  int rc = algdist_load_impl(st, xn, xe, mem, prestaged);
   for (int t = 0; rc == HGE_OK && t < iterations; ++t) {
     rc = hge_algdist_node_half(st, t);
     if (rc == HGE_OK) rc = hge_algdist_edge_half(st, t);
@@ -1176,6 +1182,44 @@ int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int 
             lohi[((size_t)t * 2 + k) * R + c] = hge_dec(h[((size_t)t * 2 + k) * st->ld + c]);
     }
   }
+  return rc;
+}
+
+int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R, int iterations,
+                    int mem, float* lohi) {
+  HGE_REQUIRE(ctx && inc && xn && xe, "hge_algdist_run: NULL argument");
+  HGE_REQUIRE(iterations >= 0, "hge_algdist_run: negative iteration count");
+  if (iterations == 0) return HGE_OK;  // the initial vectors are the result
+  return algdist_run_impl(ctx, inc, xn, xe, R, iterations, mem, lohi, false);
+}
+
+// Incidence set-up + relaxation in one call.  With host buffers the upload of the vectors is
+// queued (copy stream) right behind the upload of the column ids, BEFORE the set-up's host waits:
+// the transpose, the degree sorts and the schedule build then run under the 192 MB of vector
+// upload instead of in front of it (hge_incidence_create + hge_algdist_run leave PCIe idle there,
+// because the second call is only made when the first has returned).
+int hge_algdist_run_csr(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges, const int64_t* n2e_ptr,
+                        const int32_t* n2e_idx, const int64_t* e2n_ptr, const int32_t* e2n_idx, float* xn,
+                        float* xe, int R, int iterations, int mem, float* lohi) {
+  HGE_REQUIRE(ctx && xn && xe, "hge_algdist_run_csr: NULL argument");
+  HGE_REQUIRE(iterations >= 0, "hge_algdist_run_csr: negative iteration count");
+  HGE_REQUIRE(R >= 1 && R <= 1024, "hge_algdist_run_csr: dimension %d not in [1, 1024]", R);
+  hge_incidence* inc = nullptr;
+  const bool overlap = mem == HGE_MEM_HOST && iterations > 0;
+  HGE_TRY(incidence_create_impl(ctx, num_nodes, num_edges, n2e_ptr, n2e_idx, e2n_ptr, e2n_idx, false, 1, mem,
+                                &inc, overlap));
+  int rc = HGE_OK;
+  if (overlap) {
+    rc = stage_vectors(ctx, num_nodes, num_edges, R, xn, xe);
+    if (rc == HGE_OK) rc = incidence_finish(inc);
+  }
+  if (rc == HGE_OK && iterations > 0) rc = algdist_run_impl(ctx, inc, xn, xe, R, iterations, mem, lohi, overlap);
+  if (rc != HGE_OK && overlap) {
+    // nothing may still be reading the caller's buffers when an error is returned
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  hge_incidence_destroy(inc);
   return rc;
 }
 

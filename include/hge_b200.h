@@ -126,6 +126,14 @@ int64_t hge_incidence_nnz(const hge_incidence* inc);
  * lohi (optional, host, [iterations][2][R]) receives each sweep's per-column (min, max). */
 int hge_algdist_run(hge_ctx* ctx, hge_incidence* inc, float* xn, float* xe, int R,
                     int iterations, int mem, float* lohi);
+/* The same relaxation straight from the CSR arrays: hge_incidence_create + hge_algdist_run +
+ * hge_incidence_destroy in one call -- what EmbedAlgebraicDistance (algebraic_distance.py:126-175)
+ * does per call.  With host buffers the vectors' upload is queued behind the column ids' and the
+ * set-up kernels (transpose, schedules) run under it.  e2n_ptr / e2n_idx may be NULL (the
+ * edge -> node orientation is then built on the device). */
+int hge_algdist_run_csr(hge_ctx* ctx, int32_t num_nodes, int32_t num_edges, const int64_t* n2e_ptr,
+                        const int32_t* n2e_idx, const int64_t* e2n_ptr, const int32_t* e2n_idx, float* xn,
+                        float* xe, int R, int iterations, int mem, float* lohi);
 
 /* _helper_scale_embeddings (algebraic_distance.py:97-123) on its own: joint per-column min / max
  * of the two dense blocks, x <- (x - min) / (max - min), in place.  (hge_algdist_run fuses this

@@ -123,6 +123,50 @@ def test_long_rows_and_device_pointers(device, gpu_ctx):
   assert np.allclose(both.min(0), 0, atol=1e-6) and np.allclose(both.max(0), 1, atol=1e-6)
 
 
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("both", [False, True])
+def test_one_call_from_csr_equals_the_two_call_path(device, both, gpu_ctx):
+  """hge_algdist_run_csr (incidence set-up + relaxation in one call; with host buffers the
+  vectors' upload overlaps the set-up) gives the bits of hge_incidence_create + hge_algdist_run,
+  with one orientation or both supplied, from host or device arrays; twice in a row (the staging
+  block and the workspace pool are re-used); an isolated edge raises as the reference does."""
+  import torch
+  from hypergraphembedding_b200 import _native
+  from hypergraphembedding_b200.hypergraph_util import csr_arrays
+  rng = np.random.default_rng(17)
+  A = _random_graph(rng, 20000, 700, 150000)
+  B = A.T.tocsr()
+  B.sort_indices()
+  R, iters = 32, 7
+  xn0 = rng.random((A.shape[0], R)).astype(np.float32)
+  xe0 = rng.random((A.shape[1], R)).astype(np.float32)
+  want_n, want_e = _run(A, xn0, xe0, iters, gpu_ctx)
+  a_ptr, a_idx = csr_arrays(A)
+  b_ptr, b_idx = csr_arrays(B)
+  for rep in range(2):
+    if device:
+      dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+      xn, xe = dev(xn0), dev(xe0)
+      args = [dev(a_ptr.astype(np.int64)), dev(a_idx.astype(np.int32))]
+      kw = dict(e2n_ptr=dev(b_ptr.astype(np.int64)), e2n_idx=dev(b_idx.astype(np.int32))) if both else {}
+    else:
+      xn, xe = xn0.copy(), xe0.copy()
+      args, kw = [a_ptr, a_idx], (dict(e2n_ptr=b_ptr, e2n_idx=b_idx) if both else {})
+    lohi = np.zeros((iters, 2, R), np.float32)
+    _native.algdist_run_csr(gpu_ctx, A.shape[0], A.shape[1], args[0], args[1], xn, xe, iters, lohi=lohi, **kw)
+    if device:
+      torch.cuda.synchronize()
+      xn, xe = xn.cpu().numpy(), xe.cpu().numpy()
+    assert np.array_equal(xn, want_n) and np.array_equal(xe, want_e), rep
+    assert np.all(lohi[:, 0] < lohi[:, 1])
+  # an edge nobody is in: 0 / 0 in the reference (algebraic_distance.py:49)
+  A2 = sps.hstack([A, sps.csr_matrix((A.shape[0], 1), dtype=A.dtype)]).tocsr()
+  p2, i2 = csr_arrays(A2)
+  with pytest.raises(ZeroDivisionError):
+    _native.algdist_run_csr(gpu_ctx, A2.shape[0], A2.shape[1], p2, i2, xn0.copy(),
+                            np.zeros((A2.shape[1], R), np.float32), iters)
+
+
 def test_tuning_knobs_do_not_change_results(gpu_ctx):
   rng = np.random.default_rng(11)
   A = _random_graph(rng, 3000, 200, 40000)
