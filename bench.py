@@ -1291,7 +1291,7 @@ def run_sharded(args, spec, world, rank, local_rank):
     r.run(h_xn.numpy(), h_xe.numpy())
     r.close()
 
-  e2e_steps = max(1, min(args.steps, 3))
+  e2e_steps = max(1, min(args.steps, 10))
   h_xn.copy_(h_xn0)
   h_xe.copy_(h_xe0)
   step_host()
@@ -1299,14 +1299,18 @@ def run_sharded(args, spec, world, rank, local_rank):
   dist.barrier()
   torch.cuda.synchronize()
   t0 = time.perf_counter()
+  step_ms = []
   for _ in range(e2e_steps):
-    step_host()
+    t1 = time.perf_counter()
+    step_host()          # returns when this rank's results are in its host buffers
+    step_ms.append((time.perf_counter() - t1) * 1e3)
   torch.cuda.synchronize()
   dist.barrier()
-  e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64,
+  e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps] + step_ms, dtype=torch.float64,
                      device="cuda")
   dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-  e2e_ms = float(e2e.item())
+  e2e_ms = float(e2e[0].item())
+  step_ms = [float(v) for v in e2e[1:].tolist()]
   h2d = A.indptr.size * 8 + A.indices.size * 4 + (xn0.size + xe0.size) * 4
   d2h = (xn0.size + xe0.size) * 4
   host_link = host_link_probe(world, rank)
@@ -1343,7 +1347,7 @@ def run_sharded(args, spec, world, rank, local_rank):
                      "ms_per_launch": launch_ms, "ms_per_sweep": sweep_ms, "sweep_phases_ms": phases},
         "cpu_baseline": None,
         "e2e": {"value": nnz_global * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
-                "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * world,
+                "ms_per_step": e2e_ms, "step_ms": step_ms, "h2d_bytes_per_step": int(h2d) * world,
                 "d2h_bytes_per_step": int(d2h) * world, "host_link_GBps": host_link,
                 "copy_floor_ms": 1e3 * (h2d / (host_link["h2d_GBps_per_rank_all_ranks_at_once"] * 1e9) +
                                         d2h / (host_link["d2h_GBps_per_rank_all_ranks_at_once"] * 1e9))},
