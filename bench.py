@@ -829,7 +829,15 @@ def run_ours(args, spec):
                    "compulsory_bytes_per_launch": compulsory_bytes_per_launch(N, E, nnz, R),
                    "compulsory_GBps": compulsory_bytes_per_launch(N, E, nnz, R) / (mean_half_ms * 1e-3) / 1e9,
                    "compulsory_frac": compulsory_bytes_per_launch(N, E, nnz, R) / (mean_half_ms * 1e-3) / 1e9 / peak,
-                   "kernel_source_sha": kernel_source_sha()},
+                   "kernel_source_sha": kernel_source_sha(),
+                   # what a kernel that does nothing but this access pattern reaches on this part
+                   # (committed microbenchmark, NOT measured in this run: `tools/roof/gather_roof c2`,
+                   # profiles/r2_gather_roof_c2.log -- config 2's row counts and gathers per row,
+                   # uniform-random ids, no padding, no row finish)
+                   "gather_roof": ({"node_half_ms": 0.110, "edge_half_ms": 0.132,
+                                    "frac_node_half": 0.110 / node_ms, "frac_edge_half": 0.132 / edge_ms,
+                                    "source": "profiles/r2_half_sweep.md section 3"}
+                                   if args.workload == "c2" else None)},
       "cpu_baseline": {"value": cpu_value, "unit": "nnz*R*iters/s", "cores": cpu_threads,
                        "kind": "port",
                        "sample": "the full workload, %d of %d sweeps, C restatement of the reference's "

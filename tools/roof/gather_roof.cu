@@ -98,6 +98,50 @@ __global__ void __launch_bounds__(256, 4) k_mix_hint(const float4* __restrict__ 
   }
 }
 
+// The mix with config 2's own shape: ROUNDS rounds of 10 gathers per owned row (node half: 1M
+// rows x 10 gathers from the 64 MB edge block; edge half: 500K rows x 20 gathers from the 128 MB
+// node block), row read, row written.
+template <int ROUNDS>
+__global__ void __launch_bounds__(256, 4) k_mix_c2(const float4* __restrict__ table,
+                                                  const uint32_t* __restrict__ ids, float4* own,
+                                                  long long rows_per_warp) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t* p = ids + warp * rows_per_warp * (10 * ROUNDS) * 4 + g;
+  for (long long i = 0; i < rows_per_warp; ++i) {
+    const size_t orow = (size_t)((warp * rows_per_warp + i) * 4 + g);
+    float4 acc = __ldcs(own + orow * 8 + gl);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      float4 v[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        const uint32_t c = __ldcs(p + ((i * ROUNDS + r) * 10 + u) * 4);
+        v[u] = __ldg(table + (size_t)c * 8 + gl);
+      }
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+    __stcs(own + orow * 8 + gl, acc);
+  }
+}
+
+template <int ROUNDS>
+float run_c2(const float4* table, const uint32_t* ids, float4* own, long long own_rows, int blocks) {
+  const long long rpw = own_rows / 4 / ((long long)blocks * 8);
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  k_mix_c2<ROUNDS><<<blocks, 256>>>(table, ids, own, rpw);
+  CK(cudaEventRecord(a));
+  for (int r = 0; r < 5; ++r) k_mix_c2<ROUNDS><<<blocks, 256>>>(table, ids, own, rpw);
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  float ms; CK(cudaEventElapsedTime(&ms, a, b));
+  return ms / 5 * (float)((double)own_rows / ((double)rpw * 4 * blocks * 8));
+}
+
 __global__ void k_fill_ids(uint32_t* ids, long long n, uint32_t rows, uint64_t seed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint64_t x = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;
@@ -119,9 +163,36 @@ float run(const float4* table, const uint32_t* ids, long long per_warp, int bloc
   return ms / 5;
 }
 
-int main() {
+// config 2's own shape, uniform-random ids
+static void c2_section(int sms) {
+  {
+    printf("\nconfig-2 shape (uniform-random ids; the real edge sizes are heavy-tailed, which L1 / L2 like better):\n");
+    float4 *tn, *te, *own;
+    uint32_t* idc;
+    CK(cudaMalloc(&tn, 128ull << 20)); CK(cudaMalloc(&te, 64ull << 20)); CK(cudaMalloc(&own, 128ull << 20));
+    CK(cudaMemset(tn, 0, 128ull << 20)); CK(cudaMemset(te, 0, 64ull << 20)); CK(cudaMemset(own, 0, 128ull << 20));
+    CK(cudaMalloc(&idc, 10ll * (1 << 20) * 4));
+    for (int bps : {4, 8}) {
+      k_fill_ids<<<sms * 8, 256>>>(idc, 10ll << 20, (64u << 20) / 128, 777);
+      CK(cudaDeviceSynchronize());
+      const float node = run_c2<1>(te, idc, own, 1ll << 20, sms * bps);
+      k_fill_ids<<<sms * 8, 256>>>(idc, 10ll << 20, (128u << 20) / 128, 778);
+      CK(cudaDeviceSynchronize());
+      const float edge = run_c2<2>(tn, idc, own, 1ll << 19, sms * bps);
+      printf("blocks/SM %d  node half (1M rows x 10 gathers, 64 MB table): %.4f ms   edge half (512K rows x 20 gathers, 128 MB table): %.4f ms\n",
+             bps, node, edge);
+    }
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool only_c2 = argc > 1;   // any argument: the config-2 section only
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
+  if (only_c2) {
+    c2_section(sms);
+    return 0;
+  }
   const long long total_gathers = 16ll << 20;            // 16M rows = 2 GB gathered per launch
   uint32_t* ids; CK(cudaMalloc(&ids, total_gathers * 4));
   float4* out; CK(cudaMalloc(&out, 64));
@@ -200,5 +271,6 @@ int main() {
       CK(cudaFree(table));
     }
   }
+  c2_section(sms);
   return 0;
 }
