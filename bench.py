@@ -269,6 +269,22 @@ def cpu_baseline_scipy(A, B, spec, sweeps=2):
                     % (sweeps, spec["sweeps"], dt)}
 
 
+def workload_config(spec, world, N, E, R, sweeps):
+  """`config` of a bench line -- the workload and the cache policy of the measurement, nothing
+  run-specific -- so that the two arms (ours, --impl reference) print the same object at every N.
+  At N > 1 the workload is N config-2-shaped blocks of node rows (seeds seed .. seed + N - 1)
+  over the same edges; per-run figures (incidence counts, exchange strategy) are top-level keys
+  of our line (`detail`)."""
+  if world == 1:
+    return {"workload": spec["name"], "nodes": int(N), "edges": int(E), "R": int(R), "sweeps": int(sweeps),
+            "seed": spec["seed"],
+            "l2": "no flush: the per-step working set (vectors %d MB + incidence ~%d MB) exceeds the 126 MB L2"
+                  % ((N + E) * R * 4 >> 20, 2 * spec["num_incidences"] * 4 >> 20)}
+  return {"workload": "%d x [%s] node blocks over the same %d edges" % (world, spec["name"], E),
+          "nodes": int(N) * world, "edges": int(E), "R": int(R), "sweeps": int(sweeps), "seed": spec["seed"],
+          "l2": "no flush: per-GPU working set exceeds the 126 MB L2"}
+
+
 def run_reference(args, spec):
   """--impl reference: the reference's CPU implementation of the path on this box's host cores.
   The reference is pure Python (there is nothing of it to compile into oracle/_ref) and its
@@ -287,14 +303,18 @@ def run_reference(args, spec):
     vals.append(v)
     secs.append(dt)
   value = float(A.nnz * spec["R"] * sweeps * len(secs) / sum(secs))
+  world = max(1, int(args.gpus))
   sample = "the full workload (%d sweeps) per step" % sweeps
+  if world > 1:
+    sample = ("one of the %d node blocks (the block of seed %d: %d incidences, %d sweeps) per step -- the CPU "
+              "rate per incidence does not depend on how many blocks are stacked" % (world, spec["seed"], A.nnz, sweeps))
   out = {
       "impl": "reference", "metric": "alg-dist incidence nnz*R*iters/sec", "value": value,
       "unit": "nnz*R*iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-      "config": {"workload": spec["name"], "nodes": int(A.shape[0]), "edges": int(A.shape[1]),
-                 "nnz": int(A.nnz), "R": spec["R"], "sweeps": sweeps, "seed": spec["seed"]},
+      "config": workload_config(spec, world, A.shape[0], A.shape[1], spec["R"], sweeps),
+      "detail": {"nnz_of_the_sample": int(A.nnz)},
       "cpu_baseline": {"value": value, "unit": "nnz*R*iters/s", "cores": threads, "kind": "port",
                        "sample": sample, "host_cores": os.cpu_count()},
       "e2e": {"value": value, "unit": "nnz*R*iters/s", "h2d_bytes_per_step": 0,
@@ -810,11 +830,8 @@ def run_ours(args, spec):
       "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
-      "config": {"workload": spec["name"], "nodes": N, "edges": E, "nnz": nnz, "R": R,
-                 "sweeps": sweeps, "seed": spec["seed"],
-                 "l2": "no flush: per-step working set (vectors %d MB + incidence %d MB) exceeds the 126 MB L2"
-                       % ((N + E) * R * 4 >> 20, (2 * nnz * 4) >> 20),
-                 "device_vs_host_arm_identical": same},
+      "config": workload_config(spec, 1, N, E, R, sweeps),
+      "detail": {"nnz": nnz, "device_vs_host_arm_identical": same},
       "parity": parity,
       "roofline": {"bound": "hbm", "kernel": "k_sweep<8, node | edge>", "achieved": achieved, "peak": peak,
                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -1294,10 +1311,14 @@ def run_sharded(args, spec, world, rank, local_rank):
   h_csr = [pin(A.indptr.astype(np.int64)), pin(A.indices.astype(np.int32))]   # one orientation
 
   def step_host():
+    t_a = time.perf_counter()
     r = hd.ShardedRelaxation(None, R, sweeps, num_slices=args.slices, comm=args.comm, ctx=ctx,
                              shape=(n_loc, E), csr_host=[t.numpy() for t in h_csr])
+    t_b = time.perf_counter()
     r.run(h_xn.numpy(), h_xe.numpy())
+    t_c = time.perf_counter()
     r.close()
+    return (t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (time.perf_counter() - t_c) * 1e3
 
   e2e_steps = max(1, min(args.steps, 10))
   h_xn.copy_(h_xn0)
@@ -1307,10 +1328,10 @@ def run_sharded(args, spec, world, rank, local_rank):
   dist.barrier()
   torch.cuda.synchronize()
   t0 = time.perf_counter()
-  step_ms = []
+  step_ms, split = [], []
   for _ in range(e2e_steps):
     t1 = time.perf_counter()
-    step_host()          # returns when this rank's results are in its host buffers
+    split.append(step_host())    # returns when this rank's results are in its host buffers
     step_ms.append((time.perf_counter() - t1) * 1e3)
   torch.cuda.synchronize()
   dist.barrier()
@@ -1318,6 +1339,8 @@ def run_sharded(args, spec, world, rank, local_rank):
                      device="cuda")
   dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
   e2e_ms = float(e2e[0].item())
+  slowest = int(np.argmax(step_ms))       # this rank's slowest step: set-up / run / tear-down
+  slowest_split = dict(zip(("construct_ms", "run_ms", "close_ms"), [round(v, 2) for v in split[slowest]]))
   step_ms = [float(v) for v in e2e[1:].tolist()]
   h2d = A.indptr.size * 8 + A.indices.size * 4 + (xn0.size + xe0.size) * 4
   d2h = (xn0.size + xe0.size) * 4
@@ -1338,16 +1361,13 @@ def run_sharded(args, spec, world, rank, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%d x [%s] node blocks over the same %d edges" % (world, spec["name"], E),
-                   "nodes": n_loc * world, "edges": E, "nnz": nnz_global, "nnz_per_gpu": nnz_local,
-                   "R": R, "sweeps": sweeps, "seed": spec["seed"], "slices": args.slices,
-                   "exchange": comm,
+        "config": workload_config(spec, world, n_loc, E, R, sweeps),
+        "detail": {"nnz": nnz_global, "nnz_per_gpu": nnz_local, "slices": args.slices, "exchange": comm,
                    "partition": "nodes row-partitioned, edge block replicated; per sweep: reduce-scatter of "
                                 "the E x R partial sums to the owning GPU, all-gather of the updated edge "
                                 "rows, all-reduce(min/max) of 2R bounds -- " +
                                 ("stores to peer memory from inside the kernels + flag barriers"
                                  if comm == "p2p" else "NCCL all-reduce between the kernels"),
-                   "l2": "no flush: per-GPU working set exceeds the 126 MB L2",
                    "device_vs_host_arm_identical": same},
         "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -1355,7 +1375,9 @@ def run_sharded(args, spec, world, rank, local_rank):
                      "ms_per_launch": launch_ms, "ms_per_sweep": sweep_ms, "sweep_phases_ms": phases},
         "cpu_baseline": None,
         "e2e": {"value": nnz_global * R * sweeps / (e2e_ms * 1e-3), "unit": "nnz*R*iters/s",
-                "ms_per_step": e2e_ms, "step_ms": step_ms, "h2d_bytes_per_step": int(h2d) * world,
+                "ms_per_step": e2e_ms, "step_ms": step_ms, "median_step_ms": float(np.median(step_ms)),
+                "slowest_step_rank0": slowest_split,
+                "h2d_bytes_per_step": int(h2d) * world,
                 "d2h_bytes_per_step": int(d2h) * world, "host_link_GBps": host_link,
                 "copy_floor_ms": 1e3 * (h2d / (host_link["h2d_GBps_per_rank_all_ranks_at_once"] * 1e9) +
                                         d2h / (host_link["d2h_GBps_per_rank_all_ranks_at_once"] * 1e9))},

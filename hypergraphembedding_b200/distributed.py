@@ -18,6 +18,8 @@ sums.  Nothing else crosses GPUs: the 8.3 GB of node rows of config 5 never move
 ``NativeOps`` (libhge_b200.so).  tests/test_distributed_gloo.py drives the same orchestration
 over ``gloo`` on CPU with a numpy stand-in for the kernels (test infrastructure, not a fallback).
 """
+import os
+
 import numpy as np
 import scipy.sparse as sps
 
@@ -55,6 +57,15 @@ class _CudaView(object):
 # relaxations of the same shape; all ranks run the same call sequence, so they hit and miss the
 # pool together.  release_peer_arenas() is the collective tear-down.
 _ARENA_POOL = {}
+_STATUS_CHANNEL = {}
+
+
+def _status_channel(torch):
+  """(side stream, int32[1] device tensor) of the current device for the status agreements."""
+  dev = torch.cuda.current_device()
+  if dev not in _STATUS_CHANNEL:
+    _STATUS_CHANNEL[dev] = (torch.cuda.Stream(device=dev), torch.zeros(1, dtype=torch.int32, device="cuda"))
+  return _STATUS_CHANNEL[dev]
 _TOPOLOGY_OK = {}
 
 
@@ -274,11 +285,21 @@ class ShardedRelaxation(object):
       error, code = exc, 1
     except Exception as exc:       # noqa: BLE001 -- re-raised below, on every rank
       error, code = exc, 2
-    status = torch.tensor([code], dtype=torch.int32)
     if dist.get_backend(self.group) == "nccl":
-      status = status.cuda()
-    dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
-    worst = int(status.item())
+      # The outcome of fn is known on the host; the agreement must not wait for the set-up work fn
+      # queued on the main stream (a .item() there drains the whole pipeline three times per
+      # construction and was the source of 10-30 ms hiccups of the host-buffer step).  It runs on
+      # a side stream with a persistent status word: NCCL orders the collective after that stream
+      # only, and .item() synchronises that stream only.
+      side, status = _status_channel(torch)
+      with torch.cuda.stream(side):
+        status.fill_(code)
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        worst = int(status.item())
+    else:
+      status = torch.tensor([code], dtype=torch.int32)
+      dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+      worst = int(status.item())
     if error is not None:
       raise error
     if worst == 1:

@@ -38,6 +38,20 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
   assert d["config"]["workload"] and d["vs_baseline"] is None
 
 
+def test_both_arms_print_the_same_config_object():
+  """`config` names the workload and the cache policy only, built by one function for both arms
+  (ours and --impl reference) at every N; run-specific figures live under `detail`."""
+  import bench
+  spec = bench.WORKLOADS["c2"]
+  one = bench.workload_config(spec, 1, 1000000, 500000, 32, 20)
+  assert set(one) == {"workload", "nodes", "edges", "R", "sweeps", "seed", "l2"}
+  assert one["workload"] == spec["name"] and one["nodes"] == 1000000
+  eight = bench.workload_config(spec, 8, 1000000, 500000, 32, 20)
+  assert eight["nodes"] == 8000000 and eight["workload"].startswith("8 x [")
+  src = open(os.path.join(ROOT, "bench.py")).read()
+  assert src.count('"config": workload_config(') == 3      # reference arm, one GPU, N GPUs
+
+
 def test_other_ranks_of_the_reference_arm_stay_silent(tmp_path):
   env = dict(os.environ, HGE_CACHE_DIR=str(tmp_path), RANK="1", WORLD_SIZE="2")
   out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",

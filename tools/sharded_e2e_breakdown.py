@@ -35,7 +35,9 @@ def main():
     torch.cuda.synchronize()
     marks.append((name, time.perf_counter()))
 
-  for rep in range(4):
+  reps = int(os.environ.get("HGE_BREAKDOWN_REPS", "4"))
+  history = []
+  for rep in range(reps):
     dist.barrier()
     torch.cuda.synchronize()
     marks.clear()
@@ -62,7 +64,8 @@ def main():
     mark("store (D2H)")
     ops.close()
     mark("close")
-    if rep >= 2:
+    history.append([(n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])])
+    if rep >= 2 and reps <= 4:
       line = "rank %d rep %d: " % (rank, rep) + ", ".join(
           "%s %.2f ms" % (n, (t - marks[i][1]) * 1e3) for i, (n, t) in enumerate(marks[1:])) + \
           " | total %.2f ms" % ((marks[-1][1] - marks[0][1]) * 1e3)
@@ -70,6 +73,19 @@ def main():
       dist.all_gather_object(lines, line)
       if rank == 0:
         print("\n".join(lines), flush=True)
+  if reps > 4:
+    # many repetitions: the median step and every step that took 1.5 x the median, phase by phase
+    totals = np.asarray([sum(v for _, v in h) for h in history[2:]])
+    med = float(np.median(totals))
+    lines = ["rank %d: median step %.2f ms over %d reps" % (rank, med, len(totals))]
+    for k, h in enumerate(history[2:]):
+      if totals[k] > 1.5 * med:
+        lines.append("rank %d rep %d: %.1f ms = " % (rank, k + 2, totals[k]) +
+                     ", ".join("%s %.2f" % (n, v) for n, v in h))
+    every = [None] * world
+    dist.all_gather_object(every, "\n".join(lines))
+    if rank == 0:
+      print("\n".join(every), flush=True)
   # the public path (ShardedRelaxation: the same steps plus the status agreements)
   for rep in range(3):
     dist.barrier()
