@@ -8,18 +8,28 @@ store) of the BASELINE.json configs[1] workload: synthetic power-law hypergraph,
 500K edges / ~10M incidences, R = 32 trial columns, 20 sweeps.  Prints ONE JSON line.
 
 `value`     device-resident: vectors and incidence already in HBM when the timed region starts.
-`e2e`       the same step through the host-buffer C-ABI call (hge_incidence_create +
-            hge_algdist_run with HGE_MEM_HOST): pinned host -> device copies of the incidence
-            arrays and the initial vectors and the device -> host copy of the result are inside
-            the timed region.
+`e2e`       the same step through the host-buffer C-ABI call (hge_algdist_run_csr with
+            HGE_MEM_HOST: what EmbedAlgebraicDistance makes per hypergraph): pinned host -> device
+            copies of the incidence arrays and the initial vectors and the device -> host copy of
+            the result are inside the timed region.  N > 1: ShardedRelaxation from host buffers,
+            with the per-step times, their median and the measured host-link rates beside it.
+`parity`    the result of the timed configuration against the f64 C port of the reference's
+            arithmetic (N = 1: full size; N > 1: an N-rank relaxation against oracle/port.py).
 `roofline`  the half-sweep kernel: algorithmic bytes per launch / its mean launch
             duration measured with CUDA events on the launch stream, against the measured HBM
-            copy peak in MEASURED_PEAKS.json.
+            copy peak in MEASURED_PEAKS.json; next to it the DRAM traffic of the committed ncu
+            capture (while the kernel's sources still hash to it), the compulsory bytes, and the
+            gather-only roof of the access pattern.  N > 1: the phase split of a sweep.
 `cpu_baseline` the oracle port (oracle/algdist_ref.c: the reference's per-row f64 arithmetic, all
             host threads) on the same workload, timed on this box's host cores.  Reported, not
             the target.
-`hobe`, `pair_weighting`  the other half of BASELINE.json's metric (HOBE weighted samples/s on
-            configs[0]) and the 100M-pair weighting of configs[2].
+`config`    the workload and the cache policy only -- the same object in both arms at every N;
+            run-specific figures (incidence counts, exchange strategy) are under `detail`.
+`hobe`, `hobe_scale`, `fobe_scale`, `hg2v_train`, `c1_end_to_end`, `pair_weighting`, `c5`
+            the other half of BASELINE.json's metric (HOBE / FOBE samples/s on configs[0] and at
+            100 000 - 1 000 000 nodes, with oracle digests), the consumer of the samples,
+            configs[0] end to end, the 100M-pair weighting of configs[2] and configs[4]
+            (strong scaling at N > 1), each with its own parity check.
 """
 import argparse
 import json
